@@ -1,0 +1,592 @@
+// bsr_api.cu -- host side of the C ABI declared in include/bsr.h.
+// Plain CUDA runtime; no torch types cross this boundary.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/bsr.h"
+#include "bsr_kernels.cuh"
+
+using namespace bsr;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(expr)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (expr);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(e_ == cudaErrorMemoryAllocation ? BSR_ERR_OOM : BSR_ERR_CUDA,     \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                        \
+    } while (0)
+
+#define CHECK(cond, code, ...) \
+    do {                       \
+        if (!(cond)) return fail(code, __VA_ARGS__); \
+    } while (0)
+
+#define TRY(expr)              \
+    do {                       \
+        int rc_ = (expr);      \
+        if (rc_ != BSR_OK) return rc_; \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// the store handle
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct bsr_store {
+    int device = 0;
+    u32 dim = 0, dq = 0;
+    bsr_dtype dtype = BSR_F32;
+    u64 row_base = 0;
+    u64 n_rows = 0;
+    u64 cap_rows = 0;  // multiple of 32
+    float4* panels = nullptr;
+    float* norms = nullptr;
+    cudaStream_t stream = nullptr;
+    int n_sm = 0;
+    size_t smem_optin = 0;
+
+    // per-search scratch (grown on demand)
+    DevBuf cta_keys, merge_a, merge_b, d_queries, d_qnorm, d_cand, d_idx, d_dist, d_count, staging;
+    void* h_pinned = nullptr;
+    size_t h_pinned_bytes = 0;
+
+    u64 launches = 0;
+    cudaEvent_t ev_scan0 = nullptr, ev_scan1 = nullptr;
+    bool scan_timed = false;
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static int ensure(DevBuf& b, size_t bytes) {
+    if (b.bytes >= bytes) return BSR_OK;
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr;
+    b.bytes = 0;
+    size_t want = std::max(bytes, (size_t)256);
+    CU(cudaMalloc(&b.p, want));
+    b.bytes = want;
+    return BSR_OK;
+}
+
+static int ensure_pinned(bsr_store* s, size_t bytes) {
+    if (s->h_pinned_bytes >= bytes) return BSR_OK;
+    if (s->h_pinned) CU(cudaFreeHost(s->h_pinned));
+    s->h_pinned = nullptr;
+    s->h_pinned_bytes = 0;
+    CU(cudaMallocHost(&s->h_pinned, bytes));
+    s->h_pinned_bytes = bytes;
+    return BSR_OK;
+}
+
+static u32 next_pow2(u32 v) {
+    u32 p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static size_t panel_bytes(const bsr_store* s) { return (size_t)s->dq * 32 * sizeof(float4); }
+
+// grow the panel/norm allocation to hold at least `rows` rows, preserving contents
+static int reserve_rows(bsr_store* s, u64 rows) {
+    if (rows <= s->cap_rows) return BSR_OK;
+    u64 want = std::max(rows, s->cap_rows + s->cap_rows / 2);
+    want = (want + 31) & ~31ull;
+    const size_t pb = panel_bytes(s);
+    float4* np = nullptr;
+    float* nn = nullptr;
+    CU(cudaMalloc((void**)&np, (size_t)(want / 32) * pb));
+    cudaError_t e = cudaMalloc((void**)&nn, (size_t)want * sizeof(float));
+    if (e != cudaSuccess) {
+        cudaFree(np);
+        return fail(BSR_ERR_OOM, "cudaMalloc(norms) failed: %s", cudaGetErrorString(e));
+    }
+    const size_t used_panels = (size_t)((s->n_rows + 31) / 32);
+    if (used_panels) {
+        CU(cudaMemcpyAsync(np, s->panels, used_panels * pb, cudaMemcpyDeviceToDevice, s->stream));
+        CU(cudaMemcpyAsync(nn, s->norms, (size_t)s->n_rows * sizeof(float),
+                           cudaMemcpyDeviceToDevice, s->stream));
+    }
+    // rows past n_rows inside a used panel are already zero; zero everything newly allocated
+    CU(cudaMemsetAsync((char*)np + used_panels * pb, 0, (size_t)(want / 32 - used_panels) * pb,
+                       s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (s->panels) CU(cudaFree(s->panels));
+    if (s->norms) CU(cudaFree(s->norms));
+    s->panels = np;
+    s->norms = nn;
+    s->cap_rows = want;
+    return BSR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// library
+// ---------------------------------------------------------------------------------------------
+extern "C" int bsr_version(void) { return BSR_VERSION; }
+extern "C" const char* bsr_last_error(void) { return g_err; }
+
+extern "C" int bsr_device_count(int* n) {
+    CHECK(n, BSR_ERR_INVALID, "bsr_device_count: null output");
+    *n = 0;
+    CU(cudaGetDeviceCount(n));
+    return BSR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// store
+// ---------------------------------------------------------------------------------------------
+extern "C" int bsr_store_create(int device, uint32_t dim, bsr_dtype dtype, uint64_t row_base,
+                                uint64_t capacity_rows, bsr_store** out) {
+    CHECK(out, BSR_ERR_INVALID, "bsr_store_create: null output");
+    *out = nullptr;
+    CHECK(dim > 0, BSR_ERR_INVALID, "bsr_store_create: dim must be > 0");
+    CHECK(dtype == BSR_F32 || dtype == BSR_BF16, BSR_ERR_INVALID, "bsr_store_create: bad dtype");
+    CHECK(dtype == BSR_F32, BSR_ERR_UNSUPPORTED, "bsr_store_create: BSR_BF16 stores are not built yet");
+    CHECK(row_base < 0xFFFFFFFFull, BSR_ERR_INVALID, "bsr_store_create: row_base must fit 32 bits");
+    int n_dev = 0;
+    CU(cudaGetDeviceCount(&n_dev));
+    CHECK(device >= 0 && device < n_dev, BSR_ERR_CUDA, "bsr_store_create: no CUDA device %d (%d visible)",
+          device, n_dev);
+    DeviceGuard g(device);
+    bsr_store* s = new (std::nothrow) bsr_store();
+    CHECK(s, BSR_ERR_OOM, "bsr_store_create: host allocation failed");
+    s->device = device;
+    s->dim = dim;
+    s->dq = (dim + 3) / 4;
+    s->dtype = dtype;
+    s->row_base = row_base;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev_scan0);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev_scan1);
+    if (e != cudaSuccess) {
+        delete s;
+        return fail(BSR_ERR_CUDA, "bsr_store_create: %s", cudaGetErrorString(e));
+    }
+    s->n_sm = prop.multiProcessorCount;
+    s->smem_optin = prop.sharedMemPerBlockOptin;
+    if (capacity_rows) {
+        int rc = reserve_rows(s, capacity_rows);
+        if (rc != BSR_OK) {
+            bsr_store_destroy(s);
+            return rc;
+        }
+    }
+    *out = s;
+    return BSR_OK;
+}
+
+extern "C" int bsr_store_destroy(bsr_store* s) {
+    if (!s) return BSR_OK;
+    DeviceGuard g(s->device);
+    cudaStreamSynchronize(s->stream);
+    DevBuf* bufs[] = {&s->cta_keys, &s->merge_a, &s->merge_b, &s->d_queries, &s->d_qnorm,
+                      &s->d_cand,   &s->d_idx,   &s->d_dist,  &s->d_count,   &s->staging};
+    for (DevBuf* b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (s->panels) cudaFree(s->panels);
+    if (s->norms) cudaFree(s->norms);
+    if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    if (s->ev_scan0) cudaEventDestroy(s->ev_scan0);
+    if (s->ev_scan1) cudaEventDestroy(s->ev_scan1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return BSR_OK;
+}
+
+extern "C" int bsr_store_reset(bsr_store* s) {
+    CHECK(s, BSR_ERR_INVALID, "bsr_store_reset: null store");
+    DeviceGuard g(s->device);
+    if (s->n_rows) {
+        const size_t used_panels = (size_t)((s->n_rows + 31) / 32);
+        CU(cudaMemsetAsync(s->panels, 0, used_panels * panel_bytes(s), s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    s->n_rows = 0;
+    return BSR_OK;
+}
+
+static int check_room(bsr_store* s, u64 n_rows) {
+    CHECK(s->row_base + s->n_rows + n_rows < 0xFFFFFFFFull, BSR_ERR_RANGE,
+          "append: global row index would exceed 32 bits (row_base %llu + %llu rows)",
+          (unsigned long long)s->row_base, (unsigned long long)(s->n_rows + n_rows));
+    return BSR_OK;
+}
+
+static int finish_append(bsr_store* s, u64 n_rows) {
+    const u32 lo = (u32)s->n_rows, hi = (u32)(s->n_rows + n_rows);
+    const u32 span = hi - (lo & ~31u);
+    row_norms_kernel<<<(span + 255) / 256, 256, 0, s->stream>>>(s->panels, s->norms, lo, hi, s->dq);
+    s->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s->stream));
+    s->n_rows += n_rows;
+    return BSR_OK;
+}
+
+static int interleave_from_device(bsr_store* s, const float* d_rows, u64 row_lo, u64 n) {
+    const u32 first_panel = (u32)(row_lo >> 5);
+    const u32 last_panel = (u32)((row_lo + n - 1) >> 5);
+    const size_t total = (size_t)(last_panel - first_panel + 1) * s->dq * 128;
+    const unsigned blocks = (unsigned)((total + 1023) / 1024);
+    interleave_rows_kernel<<<blocks, 1024, 0, s->stream>>>(d_rows, (float*)s->panels, (u32)row_lo,
+                                                           (u32)n, s->dim, s->dq);
+    s->launches++;
+    CU(cudaGetLastError());
+    return BSR_OK;
+}
+
+extern "C" int bsr_store_append_device(bsr_store* s, const float* d_rows, uint64_t n_rows) {
+    CHECK(s, BSR_ERR_INVALID, "bsr_store_append_device: null store");
+    if (n_rows == 0) return BSR_OK;
+    CHECK(d_rows, BSR_ERR_INVALID, "bsr_store_append_device: null rows");
+    TRY(check_room(s, n_rows));
+    DeviceGuard g(s->device);
+    TRY(reserve_rows(s, s->n_rows + n_rows));
+    // chunk so the interleave grid stays within 32-bit thread counts
+    const u64 chunk = std::max<u64>(32, ((1ull << 30) / ((u64)s->dq * 128)) * 32);
+    for (u64 done = 0; done < n_rows; done += chunk) {
+        const u64 n = std::min(chunk, n_rows - done);
+        TRY(interleave_from_device(s, d_rows + done * s->dim, s->n_rows + done, n));
+    }
+    return finish_append(s, n_rows);
+}
+
+extern "C" int bsr_store_append(bsr_store* s, const float* rows, uint64_t n_rows) {
+    CHECK(s, BSR_ERR_INVALID, "bsr_store_append: null store");
+    if (n_rows == 0) return BSR_OK;
+    CHECK(rows, BSR_ERR_INVALID, "bsr_store_append: null rows");
+    TRY(check_room(s, n_rows));
+    DeviceGuard g(s->device);
+    TRY(reserve_rows(s, s->n_rows + n_rows));
+    const size_t row_bytes = (size_t)s->dim * sizeof(float);
+    const u64 chunk_rows = std::max<u64>(1, std::min<u64>(n_rows, (256ull << 20) / row_bytes));
+    TRY(ensure(s->staging, (size_t)chunk_rows * row_bytes));
+    for (u64 done = 0; done < n_rows; done += chunk_rows) {
+        const u64 n = std::min(chunk_rows, n_rows - done);
+        CU(cudaMemcpyAsync(s->staging.p, rows + done * s->dim, (size_t)n * row_bytes,
+                           cudaMemcpyHostToDevice, s->stream));
+        TRY(interleave_from_device(s, (const float*)s->staging.p, s->n_rows + done, n));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    return finish_append(s, n_rows);
+}
+
+extern "C" int bsr_store_append_synthetic(bsr_store* s, uint64_t seed, uint64_t first_row,
+                                          uint64_t n_rows) {
+    CHECK(s, BSR_ERR_INVALID, "bsr_store_append_synthetic: null store");
+    if (n_rows == 0) return BSR_OK;
+    TRY(check_room(s, n_rows));
+    DeviceGuard g(s->device);
+    TRY(reserve_rows(s, s->n_rows + n_rows));
+    const u64 chunk = std::max<u64>(32, ((1ull << 30) / ((u64)s->dq * 32)) * 32);
+    for (u64 done = 0; done < n_rows; done += chunk) {
+        const u64 n = std::min(chunk, n_rows - done);
+        const u64 lo = s->n_rows + done;
+        const u32 first_panel = (u32)(lo >> 5), last_panel = (u32)((lo + n - 1) >> 5);
+        const size_t total = (size_t)(last_panel - first_panel + 1) * s->dq * 32;
+        synth_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(
+            s->panels, (u32)lo, (u32)n, s->dim, s->dq, seed, first_row + done);
+        s->launches++;
+        CU(cudaGetLastError());
+    }
+    return finish_append(s, n_rows);
+}
+
+extern "C" int bsr_store_count(const bsr_store* s, uint64_t* n) {
+    CHECK(s && n, BSR_ERR_INVALID, "bsr_store_count: null argument");
+    *n = s->n_rows;
+    return BSR_OK;
+}
+extern "C" int bsr_store_dim(const bsr_store* s, uint32_t* dim) {
+    CHECK(s && dim, BSR_ERR_INVALID, "bsr_store_dim: null argument");
+    *dim = s->dim;
+    return BSR_OK;
+}
+extern "C" int bsr_store_row_base(const bsr_store* s, uint64_t* row_base) {
+    CHECK(s && row_base, BSR_ERR_INVALID, "bsr_store_row_base: null argument");
+    *row_base = s->row_base;
+    return BSR_OK;
+}
+extern "C" int bsr_store_device(const bsr_store* s, int* device) {
+    CHECK(s && device, BSR_ERR_INVALID, "bsr_store_device: null argument");
+    *device = s->device;
+    return BSR_OK;
+}
+extern "C" int bsr_store_scan_bytes(const bsr_store* s, uint64_t* bytes) {
+    CHECK(s && bytes, BSR_ERR_INVALID, "bsr_store_scan_bytes: null argument");
+    *bytes = s->n_rows * (u64)s->dq * sizeof(float4);
+    return BSR_OK;
+}
+
+extern "C" int bsr_store_get_many(const bsr_store* cs, uint64_t offset, uint64_t length,
+                                  float* out_rows) {
+    bsr_store* s = const_cast<bsr_store*>(cs);
+    CHECK(s, BSR_ERR_INVALID, "bsr_store_get_many: null store");
+    CHECK(offset <= s->n_rows && length <= s->n_rows - offset, BSR_ERR_RANGE,
+          "Index not found: rows [%llu, %llu) outside a store of %llu rows",
+          (unsigned long long)offset, (unsigned long long)(offset + length),
+          (unsigned long long)s->n_rows);
+    if (length == 0) return BSR_OK;
+    CHECK(out_rows, BSR_ERR_INVALID, "bsr_store_get_many: null output");
+    DeviceGuard g(s->device);
+    const size_t row_bytes = (size_t)s->dim * sizeof(float);
+    const u64 chunk_rows = std::max<u64>(1, std::min<u64>(length, (256ull << 20) / row_bytes));
+    TRY(ensure(s->staging, (size_t)chunk_rows * row_bytes));
+    for (u64 done = 0; done < length; done += chunk_rows) {
+        const u64 n = std::min(chunk_rows, length - done);
+        const size_t total = (size_t)n * s->dim;
+        gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(
+            (const float*)s->panels, (float*)s->staging.p, (u32)(offset + done), (u32)n, s->dim,
+            s->dq);
+        s->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out_rows + done * s->dim, s->staging.p, total * sizeof(float),
+                           cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    return BSR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// search
+// ---------------------------------------------------------------------------------------------
+extern "C" uint32_t bsr_candidate_slots(uint32_t top_k) {
+    if (top_k == 0 || top_k > BSR_MAX_TOP_K) return 0;
+    return std::max<u32>(32, next_pow2(top_k));
+}
+
+template <int U>
+static int launch_scan(bsr_store* s, const ScanArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
+    static thread_local size_t configured[64] = {0};  // per device
+    if (smem > 48 * 1024 && configured[s->device & 63] < smem) {
+        CU(cudaFuncSetAttribute(scan_topk_f32_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)s->smem_optin));
+        configured[s->device & 63] = s->smem_optin;
+    }
+    scan_topk_f32_kernel<U><<<grid, kScanThreads, smem, st>>>(a);
+    s->launches++;
+    CU(cudaGetLastError());
+    return BSR_OK;
+}
+
+// reduce n_lists lists per query to one; returns the buffer holding [nq][K] in *result
+static int merge_tree(bsr_store* s, const u64* in, u32 n_lists, u32 nq, u32 K, size_t list_stride,
+                      size_t query_stride, u64* final_out, cudaStream_t st) {
+    static thread_local bool configured[64] = {false};
+    if (!configured[s->device & 63]) {
+        CU(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(kMergeMaxKeys * sizeof(u64))));
+        configured[s->device & 63] = true;
+    }
+    const u32 max_per_cta = std::max<u32>(2, kMergeMaxKeys / K);
+    u64* ping = (u64*)s->merge_a.p;
+    u64* pong = (u64*)s->merge_b.p;
+    const u64* cur = in;
+    while (true) {
+        const u32 per_cta = std::min(max_per_cta, std::max<u32>(2, next_pow2(n_lists)));
+        const u32 groups = (n_lists + per_cta - 1) / per_cta;
+        u64* dst = (groups == 1) ? final_out : ping;
+        merge_lists_kernel<<<dim3(groups, nq), kMergeThreads, (size_t)per_cta * K * sizeof(u64), st>>>(
+            cur, n_lists, K, per_cta, list_stride, query_stride, dst);
+        s->launches++;
+        CU(cudaGetLastError());
+        if (groups == 1) break;
+        cur = dst;
+        n_lists = groups;
+        list_stride = K;
+        query_stride = (size_t)groups * K;
+        std::swap(ping, pong);
+    }
+    return BSR_OK;
+}
+
+static unsigned scan_grid(const bsr_store* s, u32 n_panels) {
+    const unsigned need = (n_panels + kScanWarps - 1) / kScanWarps;
+    return std::max(1u, std::min<unsigned>((unsigned)s->n_sm, need));
+}
+
+static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 k, u64* d_cand,
+                              cudaStream_t st) {
+    const u32 K = bsr_candidate_slots(k);
+    const u32 n_panels = (u32)((s->n_rows + 31) / 32);
+    const unsigned grid = scan_grid(s, n_panels);
+    const size_t smem = (size_t)s->dq * sizeof(float4) + (size_t)kScanWarps * K * sizeof(u64);
+    CHECK(smem <= s->smem_optin, BSR_ERR_UNSUPPORTED,
+          "search: dim %u with top_k %u needs %zu bytes of shared memory (limit %zu)", s->dim, k,
+          smem, s->smem_optin);
+    TRY(ensure(s->d_qnorm, (size_t)nq * sizeof(float)));
+    TRY(ensure(s->cta_keys, (size_t)nq * grid * K * sizeof(u64)));
+    const u32 max_per_cta = std::max<u32>(2, kMergeMaxKeys / K);
+    const size_t inter = (size_t)nq * ((grid + max_per_cta - 1) / max_per_cta) * K * sizeof(u64);
+    TRY(ensure(s->merge_a, inter));
+    TRY(ensure(s->merge_b, inter));
+
+    query_norm_kernel<<<(nq + 31) / 32, 32, 0, st>>>(d_queries, nq, s->dim, (float*)s->d_qnorm.p);
+    s->launches++;
+    CU(cudaGetLastError());
+
+    CU(cudaEventRecord(s->ev_scan0, st));
+    for (u32 q = 0; q < nq; q++) {
+        ScanArgs a;
+        a.panels = s->panels;
+        a.norms = s->norms;
+        a.query = d_queries + (size_t)q * s->dim;
+        a.qnorm = (const float*)s->d_qnorm.p + q;
+        a.cta_keys = (u64*)s->cta_keys.p + (size_t)q * grid * K;
+        a.n_rows = (u32)s->n_rows;
+        a.n_panels = n_panels;
+        a.dq = s->dq;
+        a.dim = s->dim;
+        a.k = k;
+        a.k_pad = K;
+        a.row_base = (u32)s->row_base;
+        if (s->dq % 8 == 0) TRY(launch_scan<8>(s, a, grid, smem, st));
+        else if (s->dq % 4 == 0) TRY(launch_scan<4>(s, a, grid, smem, st));
+        else if (s->dq % 2 == 0) TRY(launch_scan<2>(s, a, grid, smem, st));
+        else TRY(launch_scan<1>(s, a, grid, smem, st));
+    }
+    CU(cudaEventRecord(s->ev_scan1, st));
+    s->scan_timed = true;
+    return merge_tree(s, (const u64*)s->cta_keys.p, grid, nq, K, K, (size_t)grid * K, d_cand, st);
+}
+
+static int check_search_args(const bsr_store* s, const void* q, u32 nq, u32 k, const char* fn) {
+    CHECK(s, BSR_ERR_INVALID, "%s: null store", fn);
+    CHECK(nq == 0 || q, BSR_ERR_INVALID, "%s: null queries", fn);
+    CHECK(k >= 1 && k <= BSR_MAX_TOP_K, BSR_ERR_INVALID, "%s: top_k %u outside [1, %u]", fn, k,
+          BSR_MAX_TOP_K);
+    return BSR_OK;
+}
+
+extern "C" int bsr_search_device(bsr_store* s, const float* d_queries, uint32_t nq, uint32_t k,
+                                 uint64_t* d_candidates, void* stream) {
+    TRY(check_search_args(s, d_queries, nq, k, "bsr_search_device"));
+    if (nq == 0) return BSR_OK;
+    CHECK(d_candidates, BSR_ERR_INVALID, "bsr_search_device: null output");
+    DeviceGuard g(s->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    return search_device_impl(s, d_queries, nq, k, (u64*)d_candidates, st);
+}
+
+extern "C" int bsr_merge_device(bsr_store* s, const uint64_t* d_lists, uint32_t n_lists,
+                                uint32_t nq, uint32_t k, uint64_t* d_out, void* stream) {
+    TRY(check_search_args(s, d_lists, nq, k, "bsr_merge_device"));
+    CHECK(n_lists >= 1, BSR_ERR_INVALID, "bsr_merge_device: n_lists must be >= 1");
+    if (nq == 0) return BSR_OK;
+    CHECK(d_out, BSR_ERR_INVALID, "bsr_merge_device: null output");
+    DeviceGuard g(s->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    const u32 K = bsr_candidate_slots(k);
+    const u32 max_per_cta = std::max<u32>(2, kMergeMaxKeys / K);
+    const size_t inter = (size_t)nq * ((n_lists + max_per_cta - 1) / max_per_cta) * K * sizeof(u64);
+    TRY(ensure(s->merge_a, inter));
+    TRY(ensure(s->merge_b, inter));
+    return merge_tree(s, (const u64*)d_lists, n_lists, nq, K, (size_t)nq * K, K, (u64*)d_out, st);
+}
+
+extern "C" int bsr_unpack_device(bsr_store* s, const uint64_t* d_cand, uint32_t nq, uint32_t k,
+                                 uint64_t* d_idx, float* d_dist, uint32_t* d_count, void* stream) {
+    TRY(check_search_args(s, d_cand, nq, k, "bsr_unpack_device"));
+    if (nq == 0) return BSR_OK;
+    CHECK(d_idx && d_dist && d_count, BSR_ERR_INVALID, "bsr_unpack_device: null output");
+    DeviceGuard g(s->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    unpack_kernel<<<nq, 128, 0, st>>>((const u64*)d_cand, bsr_candidate_slots(k), k, (u64*)d_idx,
+                                      d_dist, d_count);
+    s->launches++;
+    CU(cudaGetLastError());
+    return BSR_OK;
+}
+
+extern "C" int bsr_search(bsr_store* s, const float* queries, uint32_t nq, uint32_t k,
+                          uint64_t* out_idx, float* out_dist, uint32_t* out_count) {
+    TRY(check_search_args(s, queries, nq, k, "bsr_search"));
+    if (nq == 0) return BSR_OK;
+    CHECK(out_idx && out_dist && out_count, BSR_ERR_INVALID, "bsr_search: null output");
+    DeviceGuard g(s->device);
+    const u32 K = bsr_candidate_slots(k);
+    const size_t qbytes = (size_t)nq * s->dim * sizeof(float);
+    const size_t ibytes = (size_t)nq * k * sizeof(u64), dbytes = (size_t)nq * k * sizeof(float),
+                 cbytes = (size_t)nq * sizeof(u32);
+    // pinned layout: [queries | idx | dist | count]
+    const size_t off_i = (qbytes + 15) & ~(size_t)15, off_d = off_i + ibytes, off_c = off_d + dbytes;
+    TRY(ensure_pinned(s, off_c + cbytes));
+    TRY(ensure(s->d_queries, qbytes));
+    TRY(ensure(s->d_cand, (size_t)nq * K * sizeof(u64)));
+    TRY(ensure(s->d_idx, ibytes));
+    TRY(ensure(s->d_dist, dbytes));
+    TRY(ensure(s->d_count, cbytes));
+    char* h = (char*)s->h_pinned;
+    memcpy(h, queries, qbytes);
+    CU(cudaMemcpyAsync(s->d_queries.p, h, qbytes, cudaMemcpyHostToDevice, s->stream));
+    if (s->n_rows == 0) {
+        // empty shard: compute_local_top_k returns an empty list (metrics.rs:36-52)
+        CU(cudaStreamSynchronize(s->stream));
+        memset(out_count, 0, cbytes);
+        return BSR_OK;
+    }
+    TRY(search_device_impl(s, (const float*)s->d_queries.p, nq, k, (u64*)s->d_cand.p, s->stream));
+    unpack_kernel<<<nq, 128, 0, s->stream>>>((const u64*)s->d_cand.p, K, k, (u64*)s->d_idx.p,
+                                             (float*)s->d_dist.p, (u32*)s->d_count.p);
+    s->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h + off_i, s->d_idx.p, ibytes, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(h + off_d, s->d_dist.p, dbytes, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(h + off_c, s->d_count.p, cbytes, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    memcpy(out_idx, h + off_i, ibytes);
+    memcpy(out_dist, h + off_d, dbytes);
+    memcpy(out_count, h + off_c, cbytes);
+    return BSR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// introspection
+// ---------------------------------------------------------------------------------------------
+extern "C" int bsr_store_launch_count(const bsr_store* s, uint64_t* n) {
+    CHECK(s && n, BSR_ERR_INVALID, "bsr_store_launch_count: null argument");
+    *n = s->launches;
+    return BSR_OK;
+}
+
+extern "C" int bsr_store_last_scan_ms(bsr_store* s, float* ms) {
+    CHECK(s && ms, BSR_ERR_INVALID, "bsr_store_last_scan_ms: null argument");
+    CHECK(s->scan_timed, BSR_ERR_INVALID, "bsr_store_last_scan_ms: no scan has run on this store");
+    DeviceGuard g(s->device);
+    CU(cudaEventSynchronize(s->ev_scan1));
+    CU(cudaEventElapsedTime(ms, s->ev_scan0, s->ev_scan1));
+    return BSR_OK;
+}

@@ -1,0 +1,167 @@
+/*
+ * bsr.h -- C ABI of the B200-native exact top-k search path (libbsr_b200.so).
+ *
+ * Drop-in boundary for ONE path of nichmorgan/better-search-rag-rust: the block-distributed
+ * cosine-distance scan and top-k merge.  The reference has no FFI of its own (100 % safe
+ * Rust); every entry point below names the Rust item a maintainer would re-implement on top
+ * of it (citations relative to the reference tree).  INTEGRATION.md shows the Rust binding.
+ *
+ * Conventions
+ *   - every function returns an int status: BSR_OK (0) or a negative bsr_status; nothing
+ *     unwinds across the boundary; bsr_last_error() gives a thread-local message.
+ *   - the library owns all device memory behind the opaque bsr_store handle; host buffers are
+ *     caller-owned and only borrowed for the duration of the call.
+ *   - one handle is used from one host thread at a time (the reference's caller is
+ *     single-threaded per rank, src/main.rs:25-189); distinct handles are independent.
+ *   - one handle = one shard = one GPU = one rank (reference: one MPI process,
+ *     src/mpi_helpers/metrics.rs:16-53).  Row indices reported by searches are GLOBAL:
+ *     row_base + local row, as the reference tags them (src/mpi_helpers/metrics.rs:41).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     BSR_ERR_CUDA.
+ *
+ * Results are bit-identical to the reference's CPU arithmetic (src/metrics.rs:143-165): the
+ * scan keeps the reference's strict left-to-right binary32 sums (no FMA contraction), so
+ * distances match bit for bit and ties resolve as the reference's stable sorts do (ascending
+ * global row index).
+ */
+#ifndef BSR_B200_H
+#define BSR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define BSR_API __attribute__((visibility("default")))
+#else
+#define BSR_API
+#endif
+
+#define BSR_VERSION 100 /* 0.1.0 */
+
+typedef enum bsr_status {
+    BSR_OK = 0,
+    BSR_ERR_INVALID = -1,     /* bad argument (null pointer, dim == 0, top_k out of range ...) */
+    BSR_ERR_CUDA = -2,        /* CUDA runtime error, or no usable device */
+    BSR_ERR_OOM = -3,         /* device or pinned-host allocation failed */
+    BSR_ERR_RANGE = -4,       /* row index / slice outside the store ("Index not found") */
+    BSR_ERR_UNSUPPORTED = -5  /* valid request this build does not implement */
+} bsr_status;
+
+typedef enum bsr_dtype {
+    BSR_F32 = 0, /* rows kept as binary32: the reference's own element type */
+    BSR_BF16 = 1 /* rows rounded (RNE) to bfloat16 at load: half the HBM traffic; results equal
+                    the reference arithmetic applied to the rounded rows */
+} bsr_dtype;
+
+/* Largest top_k a search accepts (per-warp candidate lists live in shared memory). */
+#define BSR_MAX_TOP_K 1024u
+
+typedef struct bsr_store bsr_store;
+
+/* ---- library ---------------------------------------------------------------------------- */
+BSR_API int bsr_version(void);
+BSR_API const char *bsr_last_error(void);
+BSR_API int bsr_device_count(int *n_devices);
+
+/* ---- store: mirrors PolarsVectorstore (src/vectorstore/polars.rs:79-247) ------------------ */
+
+/* PolarsVectorstore::new(path, empty = true) (polars.rs:80-91): an empty shard on `device`.
+ * row_base is the global index of local row 0, i.e. RankInterval::start_index of this rank
+ * (src/mpi_helpers/load_balance.rs:24-42).  capacity_rows pre-sizes the HBM allocation
+ * (0 = grow on demand). */
+BSR_API int bsr_store_create(int device, uint32_t dim, bsr_dtype dtype, uint64_t row_base,
+                     uint64_t capacity_rows, bsr_store **out);
+BSR_API int bsr_store_destroy(bsr_store *store);
+
+/* PolarsVectorstore::reset (polars.rs:93-95): drop all rows, keep the allocation. */
+BSR_API int bsr_store_reset(bsr_store *store);
+
+/* PolarsVectorstore::append_many (polars.rs:101-119): n_rows row-major rows of `dim` floats
+ * from host memory are appended to the HBM-resident shard; row norms are computed on device.
+ * append (polars.rs:97-99) is n_rows = 1. */
+BSR_API int bsr_store_append(bsr_store *store, const float *rows, uint64_t n_rows);
+
+/* Same, rows already in device memory on the store's device (row-major, 16-byte aligned). */
+BSR_API int bsr_store_append_device(bsr_store *store, const float *d_rows, uint64_t n_rows);
+
+/* Test fixture generate_mock_embeddings / sample_vstore (src/utils.rs:14-35): append n_rows
+ * uniform(-1,1) rows generated ON DEVICE by the counter-based generator documented in
+ * oracle/bsr_oracle.c (bsr_oracle_generate_rows); row r of the call is generator row
+ * first_row + r. */
+BSR_API int bsr_store_append_synthetic(bsr_store *store, uint64_t seed, uint64_t first_row,
+                               uint64_t n_rows);
+
+/* PolarsVectorstore::get_count (polars.rs:243-246). */
+BSR_API int bsr_store_count(const bsr_store *store, uint64_t *n_rows);
+BSR_API int bsr_store_dim(const bsr_store *store, uint32_t *dim);
+BSR_API int bsr_store_row_base(const bsr_store *store, uint64_t *row_base);
+BSR_API int bsr_store_device(const bsr_store *store, int *device);
+
+/* Bytes of embedding data one scan of this shard streams from HBM (rows * padded dim *
+ * sizeof(element)): the "algorithmic bytes" of DESIGN.md, excluding the norm side array. */
+BSR_API int bsr_store_scan_bytes(const bsr_store *store, uint64_t *bytes);
+
+/* PolarsVectorstore::get_many(Some(SliceArgs{offset,length})) / get (polars.rs:121-169):
+ * copy local rows [offset, offset+length) to host, row-major, bit-identical to what was
+ * appended (BSR_F32) or to its bf16 rounding (BSR_BF16).  Unlike polars' clamping slice the
+ * range must lie inside the store (BSR_ERR_RANGE otherwise: get()'s "Index not found"). */
+BSR_API int bsr_store_get_many(const bsr_store *store, uint64_t offset, uint64_t length, float *out_rows);
+
+/* ---- search: mirrors src/mpi_helpers/metrics.rs ------------------------------------------- */
+
+/* compute_local_top_k (metrics.rs:16-53) for this shard, host buffers in and out.
+ *   queries   [n_queries][dim] row-major (the reference has n_queries == 1)
+ *   out_idx   [n_queries][top_k] global row indices
+ *   out_dist  [n_queries][top_k] cosine distances (src/metrics.rs:143-165)
+ *   out_count [n_queries]        min(top_k, rows in this shard)
+ * Ascending distance, ties by ascending index (what the reference's stable sort yields).
+ * 1 <= top_k <= BSR_MAX_TOP_K. */
+BSR_API int bsr_search(bsr_store *store, const float *queries, uint32_t n_queries, uint32_t top_k,
+               uint64_t *out_idx, float *out_dist, uint32_t *out_count);
+
+/* ---- device-level pieces, for the multi-rank exchange (gather_top_k_results,
+ *      metrics.rs:56-138, becomes an all-gather of candidate slots on the host's communicator,
+ *      compute_global_top_k, metrics.rs:141-171, becomes bsr_merge_device) ------------------- */
+
+/* A candidate is one uint64: (order-preserving bits of the f32 distance) << 32 | global row
+ * index.  Unsigned ascending order of candidates == the reference's (distance, index) order.
+ * Each query owns bsr_candidate_slots(top_k) slots (a power of two >= 32); unused slots hold
+ * UINT64_MAX. */
+BSR_API uint32_t bsr_candidate_slots(uint32_t top_k);
+
+/* Scan this shard for n_queries device-resident queries; writes the shard's sorted candidates
+ * to d_candidates[n_queries][slots] on `stream` (a cudaStream_t; NULL = the store's stream).
+ * Asynchronous with respect to the host. */
+BSR_API int bsr_search_device(bsr_store *store, const float *d_queries, uint32_t n_queries,
+                      uint32_t top_k, uint64_t *d_candidates, void *stream);
+
+/* Merge n_lists candidate lists per query, laid out [n_lists][n_queries][slots] (the layout an
+ * all-gather of per-rank [n_queries][slots] buffers produces, rank-ordered as metrics.rs:86-89),
+ * into d_out[n_queries][slots].  Shards own disjoint row blocks, so candidate indices are
+ * unique by construction and the reference's HashSet de-dup (metrics.rs:156-168) is vacuous;
+ * the merge does not re-check it.  Scratch is taken from `store`. */
+BSR_API int bsr_merge_device(bsr_store *store, const uint64_t *d_lists, uint32_t n_lists,
+                     uint32_t n_queries, uint32_t top_k, uint64_t *d_out, void *stream);
+
+/* Unpack candidates[n_queries][slots] into d_idx[n_queries][top_k], d_dist[n_queries][top_k],
+ * d_count[n_queries] (all device pointers). */
+BSR_API int bsr_unpack_device(bsr_store *store, const uint64_t *d_candidates, uint32_t n_queries,
+                      uint32_t top_k, uint64_t *d_idx, float *d_dist, uint32_t *d_count,
+                      void *stream);
+
+/* ---- introspection for the benchmark harness ---------------------------------------------- */
+
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+BSR_API int bsr_store_launch_count(const bsr_store *store, uint64_t *n_launches);
+
+/* Device time of the most recent scan kernel on this handle, in milliseconds, from CUDA events
+ * recorded on the stream the kernel was launched on (synchronises that stream). */
+BSR_API int bsr_store_last_scan_ms(bsr_store *store, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSR_B200_H */
