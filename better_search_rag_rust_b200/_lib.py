@@ -66,6 +66,8 @@ SIGNATURES = {
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "bsr_store_launch_count": (C.c_int, [_store, _u64p]),
     "bsr_store_last_scan_ms": (C.c_int, [_store, _f32p]),
+    "bsr_store_set_profiling": (C.c_int, [_store, C.c_int]),
+    "bsr_store_scan_profile": (C.c_int, [_store, C.POINTER(C.c_double), _u64p]),
 }
 
 _lib = None

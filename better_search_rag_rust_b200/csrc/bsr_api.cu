@@ -5,8 +5,10 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "../../include/bsr.h"
 #include "bsr_kernels.cuh"
@@ -68,13 +70,20 @@ struct bsr_store {
     size_t smem_optin = 0;
 
     // per-search scratch (grown on demand)
-    DevBuf cta_keys, merge_a, merge_b, d_queries, d_qnorm, d_cand, d_idx, d_dist, d_count, staging;
+    DevBuf cta_keys, merge_a, merge_b, d_queries, d_cand, d_idx, d_dist, d_count, staging;
     void* h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
 
     u64 launches = 0;
     cudaEvent_t ev_scan0 = nullptr, ev_scan1 = nullptr;
     bool scan_timed = false;
+
+    // optional per-launch timing of the scan kernel (bsr_store_set_profiling)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_ev;  // pairs: [2i] before, [2i+1] after
+    size_t prof_used = 0;              // pairs recorded and not yet folded into the totals
+    double prof_ms = 0.0;
+    u64 prof_scans = 0;
 };
 
 struct DeviceGuard {
@@ -212,13 +221,14 @@ extern "C" int bsr_store_destroy(bsr_store* s) {
     if (!s) return BSR_OK;
     DeviceGuard g(s->device);
     cudaStreamSynchronize(s->stream);
-    DevBuf* bufs[] = {&s->cta_keys, &s->merge_a, &s->merge_b, &s->d_queries, &s->d_qnorm,
+    DevBuf* bufs[] = {&s->cta_keys, &s->merge_a, &s->merge_b, &s->d_queries,
                       &s->d_cand,   &s->d_idx,   &s->d_dist,  &s->d_count,   &s->staging};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (s->panels) cudaFree(s->panels);
     if (s->norms) cudaFree(s->norms);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
     if (s->ev_scan0) cudaEventDestroy(s->ev_scan0);
     if (s->ev_scan1) cudaEventDestroy(s->ev_scan1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -402,6 +412,80 @@ static int launch_scan(bsr_store* s, const ScanArgs& a, unsigned grid, size_t sm
     return BSR_OK;
 }
 
+static const size_t kProfPairs = 1024;
+
+static int prof_fold(bsr_store* s) {
+    for (size_t i = 0; i < s->prof_used; i++) {
+        float ms = 0.f;
+        CU(cudaEventSynchronize(s->prof_ev[2 * i + 1]));
+        CU(cudaEventElapsedTime(&ms, s->prof_ev[2 * i], s->prof_ev[2 * i + 1]));
+        s->prof_ms += ms;
+        s->prof_scans++;
+    }
+    s->prof_used = 0;
+    return BSR_OK;
+}
+
+static int prof_begin(bsr_store* s, cudaStream_t st) {
+    if (!s->profiling) return BSR_OK;
+    if (s->prof_used == kProfPairs) TRY(prof_fold(s));
+    while (s->prof_ev.size() < 2 * (s->prof_used + 1)) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        s->prof_ev.push_back(e);
+    }
+    CU(cudaEventRecord(s->prof_ev[2 * s->prof_used], st));
+    return BSR_OK;
+}
+
+static int prof_end(bsr_store* s, cudaStream_t st) {
+    if (!s->profiling) return BSR_OK;
+    CU(cudaEventRecord(s->prof_ev[2 * s->prof_used + 1], st));
+    s->prof_used++;
+    return BSR_OK;
+}
+
+static int scan_variant() {
+    // BSR_SCAN_VARIANT=ldg selects the register-staged kernel (ablation); default: bulk-async ring
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("BSR_SCAN_VARIANT");
+        v = (e && strcmp(e, "ldg") == 0) ? 0 : 1;
+    }
+    return v;
+}
+
+static size_t bulk_smem_bytes(const bsr_store* s, u32 K, u32 stages) {
+    return (size_t)kBulkWarps * stages * kChunkBytes + (size_t)s->dq * sizeof(float4) +
+           (size_t)kBulkWarps * K * sizeof(u64) + (size_t)kBulkWarps * stages * sizeof(u64);
+}
+
+static u32 bulk_stages(const bsr_store* s, u32 K) {
+    // 3 stages x 4 KiB x 8 warps = 96 KiB in flight per SM measured fastest on B200 (deeper rings
+    // lose bandwidth: 6 stages -7 %); BSR_BULK_STAGES overrides for tuning.
+    u32 st = 3;
+    if (const char* e = getenv("BSR_BULK_STAGES")) st = std::max(2, atoi(e));
+    while (st >= 2 && bulk_smem_bytes(s, K, st) > s->smem_optin) st--;
+    return st;  // < 2: does not fit
+}
+
+static int launch_scan_bulk(bsr_store* s, const ScanArgs& a, unsigned grid, u32 stages,
+                            cudaStream_t st) {
+    static thread_local bool configured[64] = {false};
+    if (!configured[s->device & 63]) {
+        CU(cudaFuncSetAttribute(scan_topk_f32_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)s->smem_optin));
+        configured[s->device & 63] = true;
+    }
+    BulkScanArgs ba;
+    ba.s = a;
+    ba.stages = stages;
+    scan_topk_f32_bulk_kernel<<<grid, kBulkThreads, bulk_smem_bytes(s, a.k_pad, stages), st>>>(ba);
+    s->launches++;
+    CU(cudaGetLastError());
+    return BSR_OK;
+}
+
 // reduce n_lists lists per query to one; returns the buffer holding [nq][K] in *result
 static int merge_tree(bsr_store* s, const u64* in, u32 n_lists, u32 nq, u32 K, size_t list_stride,
                       size_t query_stride, u64* final_out, cudaStream_t st) {
@@ -433,8 +517,8 @@ static int merge_tree(bsr_store* s, const u64* in, u32 n_lists, u32 nq, u32 K, s
     return BSR_OK;
 }
 
-static unsigned scan_grid(const bsr_store* s, u32 n_panels) {
-    const unsigned need = (n_panels + kScanWarps - 1) / kScanWarps;
+static unsigned scan_grid(const bsr_store* s, u32 n_panels, int warps_per_cta) {
+    const unsigned need = (n_panels + warps_per_cta - 1) / warps_per_cta;
     return std::max(1u, std::min<unsigned>((unsigned)s->n_sm, need));
 }
 
@@ -442,21 +526,18 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
                               cudaStream_t st) {
     const u32 K = bsr_candidate_slots(k);
     const u32 n_panels = (u32)((s->n_rows + 31) / 32);
-    const unsigned grid = scan_grid(s, n_panels);
+    const u32 stages = bulk_stages(s, K);
+    const bool bulk = scan_variant() == 1 && stages >= 2;
+    const unsigned grid = scan_grid(s, n_panels, bulk ? kBulkWarps : kScanWarps);
     const size_t smem = (size_t)s->dq * sizeof(float4) + (size_t)kScanWarps * K * sizeof(u64);
-    CHECK(smem <= s->smem_optin, BSR_ERR_UNSUPPORTED,
+    CHECK(bulk || smem <= s->smem_optin, BSR_ERR_UNSUPPORTED,
           "search: dim %u with top_k %u needs %zu bytes of shared memory (limit %zu)", s->dim, k,
           smem, s->smem_optin);
-    TRY(ensure(s->d_qnorm, (size_t)nq * sizeof(float)));
     TRY(ensure(s->cta_keys, (size_t)nq * grid * K * sizeof(u64)));
     const u32 max_per_cta = std::max<u32>(2, kMergeMaxKeys / K);
     const size_t inter = (size_t)nq * ((grid + max_per_cta - 1) / max_per_cta) * K * sizeof(u64);
     TRY(ensure(s->merge_a, inter));
     TRY(ensure(s->merge_b, inter));
-
-    query_norm_kernel<<<(nq + 31) / 32, 32, 0, st>>>(d_queries, nq, s->dim, (float*)s->d_qnorm.p);
-    s->launches++;
-    CU(cudaGetLastError());
 
     CU(cudaEventRecord(s->ev_scan0, st));
     for (u32 q = 0; q < nq; q++) {
@@ -464,7 +545,6 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
         a.panels = s->panels;
         a.norms = s->norms;
         a.query = d_queries + (size_t)q * s->dim;
-        a.qnorm = (const float*)s->d_qnorm.p + q;
         a.cta_keys = (u64*)s->cta_keys.p + (size_t)q * grid * K;
         a.n_rows = (u32)s->n_rows;
         a.n_panels = n_panels;
@@ -473,10 +553,16 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
         a.k = k;
         a.k_pad = K;
         a.row_base = (u32)s->row_base;
-        if (s->dq % 8 == 0) TRY(launch_scan<8>(s, a, grid, smem, st));
+        TRY(prof_begin(s, st));
+        if (bulk) TRY(launch_scan_bulk(s, a, grid, stages, st));
+        else if (s->dq % 16 == 0 && getenv("BSR_LDG_U") && atoi(getenv("BSR_LDG_U")) == 16)
+            TRY(launch_scan<16>(s, a, grid, smem, st));
+        else if (s->dq % 8 == 0 && !(getenv("BSR_LDG_U") && atoi(getenv("BSR_LDG_U")) == 4))
+            TRY(launch_scan<8>(s, a, grid, smem, st));
         else if (s->dq % 4 == 0) TRY(launch_scan<4>(s, a, grid, smem, st));
         else if (s->dq % 2 == 0) TRY(launch_scan<2>(s, a, grid, smem, st));
         else TRY(launch_scan<1>(s, a, grid, smem, st));
+        TRY(prof_end(s, st));
     }
     CU(cudaEventRecord(s->ev_scan1, st));
     s->scan_timed = true;
@@ -497,7 +583,7 @@ extern "C" int bsr_search_device(bsr_store* s, const float* d_queries, uint32_t 
     if (nq == 0) return BSR_OK;
     CHECK(d_candidates, BSR_ERR_INVALID, "bsr_search_device: null output");
     DeviceGuard g(s->device);
-    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    cudaStream_t st = (cudaStream_t)stream;
     return search_device_impl(s, d_queries, nq, k, (u64*)d_candidates, st);
 }
 
@@ -508,7 +594,7 @@ extern "C" int bsr_merge_device(bsr_store* s, const uint64_t* d_lists, uint32_t 
     if (nq == 0) return BSR_OK;
     CHECK(d_out, BSR_ERR_INVALID, "bsr_merge_device: null output");
     DeviceGuard g(s->device);
-    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    cudaStream_t st = (cudaStream_t)stream;
     const u32 K = bsr_candidate_slots(k);
     const u32 max_per_cta = std::max<u32>(2, kMergeMaxKeys / K);
     const size_t inter = (size_t)nq * ((n_lists + max_per_cta - 1) / max_per_cta) * K * sizeof(u64);
@@ -523,7 +609,7 @@ extern "C" int bsr_unpack_device(bsr_store* s, const uint64_t* d_cand, uint32_t 
     if (nq == 0) return BSR_OK;
     CHECK(d_idx && d_dist && d_count, BSR_ERR_INVALID, "bsr_unpack_device: null output");
     DeviceGuard g(s->device);
-    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    cudaStream_t st = (cudaStream_t)stream;
     unpack_kernel<<<nq, 128, 0, st>>>((const u64*)d_cand, bsr_candidate_slots(k), k, (u64*)d_idx,
                                       d_dist, d_count);
     s->launches++;
@@ -588,5 +674,24 @@ extern "C" int bsr_store_last_scan_ms(bsr_store* s, float* ms) {
     DeviceGuard g(s->device);
     CU(cudaEventSynchronize(s->ev_scan1));
     CU(cudaEventElapsedTime(ms, s->ev_scan0, s->ev_scan1));
+    return BSR_OK;
+}
+
+extern "C" int bsr_store_set_profiling(bsr_store* s, int enabled) {
+    CHECK(s, BSR_ERR_INVALID, "bsr_store_set_profiling: null store");
+    DeviceGuard g(s->device);
+    TRY(prof_fold(s));
+    s->profiling = enabled != 0;
+    s->prof_ms = 0.0;
+    s->prof_scans = 0;
+    return BSR_OK;
+}
+
+extern "C" int bsr_store_scan_profile(bsr_store* s, double* total_ms, uint64_t* n_scans) {
+    CHECK(s && total_ms && n_scans, BSR_ERR_INVALID, "bsr_store_scan_profile: null argument");
+    DeviceGuard g(s->device);
+    TRY(prof_fold(s));
+    *total_ms = s->prof_ms;
+    *n_scans = s->prof_scans;
     return BSR_OK;
 }

@@ -68,6 +68,15 @@ __device__ __forceinline__ float dot4_seq(float acc, const float4& a, const floa
     return acc;
 }
 
+// |b|^2 accumulation step for the query (src/metrics.rs:155), same sequential order
+__device__ __forceinline__ float sq4_seq(float acc, const float4& q) {
+    acc = __fadd_rn(acc, __fmul_rn(q.x, q.x));
+    acc = __fadd_rn(acc, __fmul_rn(q.y, q.y));
+    acc = __fadd_rn(acc, __fmul_rn(q.z, q.z));
+    acc = __fadd_rn(acc, __fmul_rn(q.w, q.w));
+    return acc;
+}
+
 // src/metrics.rs:13 -- `(a[i] - b[i]).abs() > 1e-10`; false for NaN.
 __device__ __forceinline__ bool differs(float a, float b) {
     return fabsf(__fsub_rn(a, b)) > 1e-10f;
@@ -84,6 +93,24 @@ __device__ __forceinline__ float finish_distance(float dot, float mag_a, float m
     float sim = __fdiv_rn(dot, __fmul_rn(mag_a, mag_b));
     sim = fminf(fmaxf(sim, -1.0f), 1.0f);  // fmaxf/fminf drop a NaN operand like f32::max/min
     return __fsub_rn(1.0f, sim);
+}
+
+// Full identity test (src/metrics.rs:7-19) for the rare rows whose first four columns already
+// match the query: the whole warp checks the flagged lane's row, 32 column-quads at a time, so
+// the test costs a couple of memory round trips instead of dq dependent ones.
+__device__ __forceinline__ bool warp_confirm_identical(bool maybe, const float4* panel_base,
+                                                       const float4* sq, u32 dq, int lane) {
+    unsigned m = __ballot_sync(0xFFFFFFFFu, maybe);
+    bool identical = false;
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        bool diff = false;
+        for (u32 j = lane; j < dq; j += 32) diff |= differs4(panel_base[(size_t)j * 32 + src], sq[j]);
+        const bool any_diff = __any_sync(0xFFFFFFFFu, diff);
+        if (lane == src) identical = !any_diff;
+    }
+    return identical;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -108,15 +135,67 @@ __device__ __forceinline__ void warp_list_insert(u64* list, int k, u64 x, int la
     tau = list[k - 1];
 }
 
-__device__ __forceinline__ void warp_offer(u64* list, int k, u64 key, int lane, u64& tau) {
-    unsigned m = __ballot_sync(0xFFFFFFFFu, key < tau);
-    while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        const u64 x = __shfl_sync(0xFFFFFFFFu, key, src);
-        if (x < tau) warp_list_insert(list, k, x, lane, tau);
+// ascending bitonic sort of K (power of two >= 32) keys in shared memory by one warp
+__device__ __forceinline__ void warp_sort_list(u64* list, u32 K, int lane) {
+    for (u32 size = 2; size <= K; size <<= 1) {
+        for (u32 d = size >> 1; d >= 1; d >>= 1) {
+            for (u32 t = lane; t < (K >> 1); t += 32) {
+                const u32 lo = ((t / d) * 2 * d) + (t % d), hi = lo + d;
+                const bool asc = (lo & size) == 0;
+                const u64 x = list[lo], y = list[hi];
+                if ((x > y) == asc) {
+                    list[lo] = y;
+                    list[hi] = x;
+                }
+            }
+            __syncwarp();
+        }
     }
 }
+
+// Per-warp running top-k.  Fill phase: the first K keys are appended unsorted and sorted once;
+// after that only keys below the current k-th best (tau) are inserted.
+struct WarpTopK {
+    u64* list;
+    int k;
+    u32 K, cnt;
+    u64 tau;
+
+    __device__ __forceinline__ void init(u64* l, u32 k_, u32 K_, int lane) {
+        list = l;
+        k = (int)k_;
+        K = K_;
+        cnt = 0;
+        tau = kKeyMax;
+        for (u32 j = lane; j < K; j += 32) list[j] = kKeyMax;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void offer(u64 key, int lane) {
+        if (cnt < K) {  // warp-uniform
+            list[cnt + lane] = key;
+            cnt += 32;
+            __syncwarp();
+            if (cnt == K) {
+                warp_sort_list(list, K, lane);
+                tau = list[k - 1];
+            }
+            return;
+        }
+        unsigned m = __ballot_sync(0xFFFFFFFFu, key < tau);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const u64 x = __shfl_sync(0xFFFFFFFFu, key, src);
+            if (x < tau) warp_list_insert(list, k, x, lane, tau);
+        }
+    }
+    __device__ __forceinline__ void finish(int lane) {
+        if (cnt < K) {
+            __syncwarp();
+            warp_sort_list(list, K, lane);
+        }
+    }
+};
 
 // ------------------------------------------------------------------------------------------
 // CTA-wide: reduce L (power of two) ascending lists of K (power of two) keys, contiguous in
@@ -159,7 +238,6 @@ struct ScanArgs {
     const float4* panels;  // [n_panels][dq][32]
     const float* norms;    // [n_rows]  |a| = sqrt(seq-sum a_i^2)  (src/metrics.rs:154)
     const float* query;    // [dim]
-    const float* qnorm;    // [1]      |b|                        (src/metrics.rs:155)
     u64* cta_keys;         // [gridDim.x][k_pad]
     u32 n_rows, n_panels, dq, dim, k, k_pad;
     u32 row_base;          // global index of local row 0
@@ -167,7 +245,7 @@ struct ScanArgs {
 
 template <int U>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_f32_kernel(const ScanArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* sq = reinterpret_cast<float4*>(smem_raw);
     u64* lists = reinterpret_cast<u64*>(smem_raw + (size_t)a.dq * sizeof(float4));
 
@@ -185,13 +263,14 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_f32_kernel(const Sc
         v.w = (c + 3 < a.dim) ? a.query[c + 3] : 0.0f;
         sq[j] = v;
     }
-    u64* wl = lists + (size_t)warp * a.k_pad;
-    for (u32 j = lane; j < a.k_pad; j += 32) wl[j] = kKeyMax;
+    WarpTopK top;
+    top.init(lists + (size_t)warp * a.k_pad, a.k, a.k_pad, lane);
     __syncthreads();
 
-    const float mag_b = *a.qnorm;
-    const int k = (int)a.k;
-    u64 tau = kKeyMax;
+    // |b| is the same for every row; each thread accumulates it (sequentially, as
+    // src/metrics.rs:155 does) alongside its first panel, from the query values it reads anyway.
+    float mag_b = 0.0f, qsq = 0.0f;
+    bool need_qnorm = true;
 
     const u32 total_warps = gridDim.x * kScanWarps;
     u32 panel = blockIdx.x * kScanWarps + warp;
@@ -228,26 +307,24 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_f32_kernel(const Sc
             }
 #pragma unroll
             for (int u = 0; u < U; u++) acc = dot4_seq(acc, cur[u], sq[j0 + u]);
+            if (need_qnorm) {
+#pragma unroll
+                for (int u = 0; u < U; u++) qsq = sq4_seq(qsq, sq[j0 + u]);
+            }
 
             if (j0 + U == dq) {
-                const u32 row = panel * kPanelRows + lane;
-                u64 key = kKeyMax;
-                if (row < a.n_rows) {
-                    bool identical = false;
-                    if (maybe_identical) {
-                        identical = true;
-                        const float4* pr = a.panels + (size_t)panel * panel_stride + lane;
-                        for (u32 j = 1; j < dq; j++) {
-                            if (differs4(pr[(size_t)j * 32], sq[j])) {
-                                identical = false;
-                                break;
-                            }
-                        }
-                    }
-                    const float dist = finish_distance(acc, mag_a, mag_b, identical);
-                    key = make_key(dist, a.row_base + row);
+                if (need_qnorm) {
+                    mag_b = __fsqrt_rn(qsq);
+                    need_qnorm = false;
                 }
-                warp_offer(wl, k, key, lane, tau);
+                const u32 row = panel * kPanelRows + lane;
+                const bool identical = warp_confirm_identical(
+                    maybe_identical && row < a.n_rows, a.panels + (size_t)panel * panel_stride, sq,
+                    dq, lane);
+                u64 key = kKeyMax;
+                if (row < a.n_rows)
+                    key = make_key(finish_distance(acc, mag_a, mag_b, identical), a.row_base + row);
+                top.offer(key, lane);
             }
             if (!has_next) break;
 #pragma unroll
@@ -256,10 +333,190 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_f32_kernel(const Sc
             panel = npanel;
         }
     }
+    top.finish(lane);
     __syncthreads();
     cta_merge_lists(lists, kScanWarps, a.k_pad);
     u64* out = a.cta_keys + (size_t)blockIdx.x * a.k_pad;
     for (u32 j = tid; j < a.k_pad; j += kScanThreads) out[j] = lists[j];
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 (bulk-async variant): the same scan, but every warp streams its panels through a private
+// shared-memory ring filled by cp.async.bulk (the TMA engine, SASS UBLKCP) and tracked by
+// mbarriers.  No registers are tied up by loads in flight, so each warp keeps `stages` x 4 KiB
+// outstanding (~190 KiB per SM): enough to hold HBM bandwidth even in the last, partially
+// filled round of panels, which is what limits small stores.
+// ------------------------------------------------------------------------------------------
+constexpr int kBulkWarps = 8;
+constexpr int kBulkThreads = kBulkWarps * 32;
+constexpr int kChunkQuads = 8;                       // column-quads per bulk copy
+constexpr int kChunkBytes = kChunkQuads * 32 * 16;   // 4 KiB
+
+__device__ __forceinline__ u32 smem_u32(const void* p) {
+    return (u32)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(u32 bar, u32 parity) {
+    u32 ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ u64 make_evict_first_policy() {
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// global -> shared bulk copy (TMA, 1-D), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(u32 dst, const void* src, u32 bytes, u32 bar, u64 policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
+
+struct BulkScanArgs {
+    ScanArgs s;
+    u32 stages;  // ring depth per warp (>= 2)
+};
+
+__global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_f32_bulk_kernel(const BulkScanArgs ba) {
+    const ScanArgs& a = ba.s;
+    constexpr int CH = kChunkQuads;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const u32 dq = a.dq, S = ba.stages;
+    // [ring: W*S*4KiB | query: dq*16 | lists: W*K*8 | mbarriers: W*S*8]
+    unsigned char* ring_all = smem_raw;
+    float4* sq = reinterpret_cast<float4*>(ring_all + (size_t)kBulkWarps * S * kChunkBytes);
+    u64* lists = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(sq) + (size_t)dq * 16);
+    u64* bars = lists + (size_t)kBulkWarps * a.k_pad;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 ring = smem_u32(ring_all + (size_t)warp * S * kChunkBytes);
+    const float4* ring_v = reinterpret_cast<const float4*>(ring_all + (size_t)warp * S * kChunkBytes);
+    const u32 bar0 = smem_u32(bars + (size_t)warp * S);
+
+    const u32 total_warps = gridDim.x * kBulkWarps;
+    const u32 panel0 = blockIdx.x * kBulkWarps + warp;
+    const u32 cpp = (dq + CH - 1) / CH;  // chunks per panel
+    const u32 my_panels = panel0 < a.n_panels ? (a.n_panels - 1 - panel0) / total_warps + 1 : 0;
+    const u32 n_chunks = my_panels * cpp;
+    const size_t panel_stride = (size_t)dq * 32;  // float4 units
+    const u64 policy = make_evict_first_policy();
+
+    // producer state (meaningful in lane 0): next chunk to request
+    u32 ic = 0, ipanel = panel0, ici = 0;
+    auto issue = [&]() {
+        const u32 nq = min((u32)CH, dq - ici * CH);
+        const u32 st = ic % S;
+        const float4* src = a.panels + (size_t)ipanel * panel_stride + (size_t)ici * CH * 32;
+        mbar_expect_tx(bar0 + st * 8, nq * 512);
+        bulk_g2s(ring + st * kChunkBytes, src, nq * 512, bar0 + st * 8, policy);
+        ic++;
+        if (++ici == cpp) {
+            ici = 0;
+            ipanel += total_warps;
+        }
+    };
+    if (lane == 0) {
+        for (u32 st = 0; st < S; st++) mbar_init(bar0 + st * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const u32 pre = min(S, n_chunks);
+        for (u32 i = 0; i < pre; i++) issue();
+    }
+
+    for (u32 j = tid; j < dq; j += kBulkThreads) {
+        const u32 c = 4 * j;
+        float4 v;
+        v.x = (c + 0 < a.dim) ? a.query[c + 0] : 0.0f;
+        v.y = (c + 1 < a.dim) ? a.query[c + 1] : 0.0f;
+        v.z = (c + 2 < a.dim) ? a.query[c + 2] : 0.0f;
+        v.w = (c + 3 < a.dim) ? a.query[c + 3] : 0.0f;
+        sq[j] = v;
+    }
+    WarpTopK top;
+    top.init(lists + (size_t)warp * a.k_pad, a.k, a.k_pad, lane);
+    __syncthreads();
+    float mag_b = 0.0f, qsq = 0.0f;  // |b|: accumulated by every thread during its first panel
+    bool need_qnorm = true;
+
+    u32 stage = 0, parity = 0, ci = 0, panel = panel0;
+    float acc = 0.0f, mag_a = 0.0f;
+    bool maybe_identical = false;
+    for (u32 c = 0; c < n_chunks; c++) {
+        const u32 j0 = ci * CH;
+        if (ci == 0) {
+            const u32 row = panel * kPanelRows + lane;
+            mag_a = (row < a.n_rows) ? __ldg(a.norms + row) : 0.0f;
+            acc = 0.0f;
+        }
+        mbar_wait(bar0 + stage * 8, parity);
+        const float4* sp = ring_v + (size_t)stage * (kChunkBytes / 16) + lane;
+        if (j0 + CH <= dq) {
+            float4 v[CH];
+#pragma unroll
+            for (int u = 0; u < CH; u++) v[u] = sp[u * 32];
+            if (ci == 0) maybe_identical = !differs4(v[0], sq[0]);
+#pragma unroll
+            for (int u = 0; u < CH; u++) acc = dot4_seq(acc, v[u], sq[j0 + u]);
+            if (need_qnorm) {
+#pragma unroll
+                for (int u = 0; u < CH; u++) qsq = sq4_seq(qsq, sq[j0 + u]);
+            }
+        } else {
+            for (u32 u = 0; j0 + u < dq; u++) {
+                const float4 v = sp[u * 32];
+                if (ci == 0 && u == 0) maybe_identical = !differs4(v, sq[0]);
+                acc = dot4_seq(acc, v, sq[j0 + u]);
+                if (need_qnorm) qsq = sq4_seq(qsq, sq[j0 + u]);
+            }
+        }
+        __syncwarp();  // every lane has consumed this stage: hand it back to the copy engine
+        if (lane == 0 && ic < n_chunks) issue();
+
+        if (++ci == cpp) {
+            if (need_qnorm) {
+                mag_b = __fsqrt_rn(qsq);
+                need_qnorm = false;
+            }
+            const u32 row = panel * kPanelRows + lane;
+            const bool identical = warp_confirm_identical(
+                maybe_identical && row < a.n_rows, a.panels + (size_t)panel * panel_stride, sq, dq,
+                lane);
+            u64 key = kKeyMax;
+            if (row < a.n_rows)
+                key = make_key(finish_distance(acc, mag_a, mag_b, identical), a.row_base + row);
+            top.offer(key, lane);
+            ci = 0;
+            panel += total_warps;
+        }
+        if (++stage == S) {
+            stage = 0;
+            parity ^= 1;
+        }
+    }
+    top.finish(lane);
+    __syncthreads();
+    cta_merge_lists(lists, kBulkWarps, a.k_pad);
+    u64* out = a.cta_keys + (size_t)blockIdx.x * a.k_pad;
+    for (u32 j = tid; j < a.k_pad; j += kBulkThreads) out[j] = lists[j];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -271,7 +528,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_f32_kernel(const Sc
 __global__ void __launch_bounds__(kMergeThreads) merge_lists_kernel(
     const u64* __restrict__ in, u32 n_lists, u32 K, u32 lists_per_cta, size_t list_stride,
     size_t query_stride, u64* __restrict__ out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     u64* buf = reinterpret_cast<u64*>(smem_raw);
     const u32 g = blockIdx.x, q = blockIdx.y;
     const u32 first = g * lists_per_cta;
@@ -305,22 +562,6 @@ __global__ void unpack_kernel(const u64* __restrict__ cand, u32 K, u32 k, u64* _
     if (valid) atomicAdd(&total, valid);
     __syncthreads();
     if (threadIdx.x == 0) count[q] = (u32)total;
-}
-
-// ------------------------------------------------------------------------------------------
-// query preparation: |b| = sqrt(sequential sum b_i^2)  (src/metrics.rs:155), one thread per query
-// ------------------------------------------------------------------------------------------
-__global__ void query_norm_kernel(const float* __restrict__ queries, u32 n_queries, u32 dim,
-                                  float* __restrict__ qnorm) {
-    const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n_queries) return;
-    const float* b = queries + (size_t)q * dim;
-    float s = 0.0f;
-    for (u32 i = 0; i < dim; i++) {
-        const float v = b[i];
-        s = __fadd_rn(s, __fmul_rn(v, v));
-    }
-    qnorm[q] = __fsqrt_rn(s);
 }
 
 // ------------------------------------------------------------------------------------------

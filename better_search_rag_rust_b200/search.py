@@ -105,9 +105,9 @@ class CudaShardEngine:
         import torch
         return torch
 
-    def search_candidates(self, queries, top_k: int):
+    def search_candidates(self, queries, top_k: int, out=None):
         """queries [nq, dim] (numpy or torch) -> int64 tensor [nq, slots] of candidate keys on the
-        shard's GPU (bit pattern of the uint64 keys)."""
+        shard's GPU (bit pattern of the uint64 keys).  `out` reuses a preallocated tensor."""
         torch = self._torch()
         dev = torch.device("cuda", self.store.device)
         slots = candidate_slots(top_k)
@@ -121,22 +121,28 @@ class CudaShardEngine:
             idx, dist, count = self.local_top_k(q.cpu().numpy(), top_k)
             keys = np.stack([pack_candidates(idx[i, :count[i]], dist[i, :count[i]], slots)
                              for i in range(nq)])
-            return torch.from_numpy(keys.view(np.int64)).to(dev)
+            res = torch.from_numpy(keys.view(np.int64)).to(dev)
+            if out is not None:
+                out.copy_(res)
+                return out
+            return res
         q = q.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
-        out = torch.empty((nq, slots), dtype=torch.int64, device=dev)
+        if out is None:
+            out = torch.empty((nq, slots), dtype=torch.int64, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(_lib.lib().bsr_search_device(self.store.handle, q.data_ptr(), nq, top_k,
                                                 out.data_ptr(), C.c_void_p(stream)))
         return out
 
-    def merge(self, lists, top_k: int):
+    def merge(self, lists, top_k: int, out=None):
         """lists [n_lists, nq, slots] int64 (any device) -> [nq, slots] on the shard's GPU."""
         torch = self._torch()
         dev = torch.device("cuda", self.store.device)
         lists = lists.to(dev).contiguous()
         n_lists, nq, slots = lists.shape
         assert slots == candidate_slots(top_k)
-        out = torch.empty((nq, slots), dtype=torch.int64, device=dev)
+        if out is None:
+            out = torch.empty((nq, slots), dtype=torch.int64, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(_lib.lib().bsr_merge_device(self.store.handle, lists.data_ptr(), n_lists, nq,
                                                top_k, out.data_ptr(), C.c_void_p(stream)))
@@ -241,9 +247,9 @@ def _all_gather(world, t):
     backend = dist.get_backend(world)
     src = t if backend == "nccl" or not t.is_cuda else t.cpu()
     src = src.contiguous()
-    out = torch.empty((size,) + tuple(src.shape), dtype=src.dtype, device=src.device)
-    dist.all_gather_into_tensor(out, src, group=world)
-    return out
+    flat = torch.empty(size * src.numel(), dtype=src.dtype, device=src.device)
+    dist.all_gather_into_tensor(flat, src.reshape(-1), group=world)
+    return flat.reshape((size,) + tuple(src.shape))
 
 
 def gather_top_k_results(world, rank: int, local_top_k: TopK):
@@ -344,7 +350,7 @@ def parallel_top_k_similarity_search(world, rank: int, size: int, vstore_dir, to
         print(f"[Rank {rank}] Error in similarity search: {err!r}")
         import torch
         cand = torch.from_numpy(np.full((1, slots), KEY_MAX, dtype=np.uint64).view(np.int64))
-        eng = engine
+        eng = engine or _merge_engine(_default_device(rank) if device is None else device)
     if size > 1:
         gathered = _all_gather(world, cand)  # [size, 1, slots], rank-ordered (:86-89)
         if not is_root(rank):

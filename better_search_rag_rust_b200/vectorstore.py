@@ -235,6 +235,15 @@ class GpuVectorstore:
         _lib.check(_lib.lib().bsr_store_launch_count(self.handle, C.byref(n)))
         return int(n.value)
 
+    def set_profiling(self, enabled: bool) -> None:
+        _lib.check(_lib.lib().bsr_store_set_profiling(self.handle, 1 if enabled else 0))
+
+    def scan_profile(self) -> tuple[float, int]:
+        """(summed scan-kernel device time in ms, number of scan launches) since set_profiling."""
+        ms, n = C.c_double(), C.c_uint64()
+        _lib.check(_lib.lib().bsr_store_scan_profile(self.handle, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
     def last_scan_ms(self) -> float:
         ms = C.c_float()
         _lib.check(_lib.lib().bsr_store_last_scan_ms(self.handle, C.byref(ms)))

@@ -133,7 +133,7 @@ BSR_API int bsr_search(bsr_store *store, const float *queries, uint32_t n_querie
 BSR_API uint32_t bsr_candidate_slots(uint32_t top_k);
 
 /* Scan this shard for n_queries device-resident queries; writes the shard's sorted candidates
- * to d_candidates[n_queries][slots] on `stream` (a cudaStream_t; NULL = the store's stream).
+ * to d_candidates[n_queries][slots] on `stream` (a cudaStream_t; NULL = the CUDA default stream, as in the runtime API).
  * Asynchronous with respect to the host. */
 BSR_API int bsr_search_device(bsr_store *store, const float *d_queries, uint32_t n_queries,
                       uint32_t top_k, uint64_t *d_candidates, void *stream);
@@ -160,6 +160,13 @@ BSR_API int bsr_store_launch_count(const bsr_store *store, uint64_t *n_launches)
 /* Device time of the most recent scan kernel on this handle, in milliseconds, from CUDA events
  * recorded on the stream the kernel was launched on (synchronises that stream). */
 BSR_API int bsr_store_last_scan_ms(bsr_store *store, float *ms);
+
+/* Per-launch timing of the scan kernel: while enabled, every scan launch is bracketed by CUDA
+ * events on the stream it is launched on (no host synchronisation at launch time).
+ * bsr_store_scan_profile synchronises, then returns the summed device time and the number of
+ * scan launches since profiling was (re-)enabled. */
+BSR_API int bsr_store_set_profiling(bsr_store *store, int enabled);
+BSR_API int bsr_store_scan_profile(bsr_store *store, double *total_ms, uint64_t *n_scans);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,96 @@
+"""CPU: host-side mirror of the reference interface (no GPU, no compute through the library)."""
+import os
+
+import numpy as np
+import pytest
+
+import better_search_rag_rust_b200 as bsr
+from better_search_rag_rust_b200 import search as S
+from better_search_rag_rust_b200 import vectorstore as V
+from oracle import c_oracle as co
+
+F = np.float32
+
+
+def test_interval_by_rank_mirrors_reference_arithmetic():
+    for count in list(range(0, 30)) + [1000, 1027, 100_000_000]:
+        for size in (1, 2, 3, 4, 7, 8, 41):
+            for rank in range(size):
+                iv = bsr.interval_by_rank(rank, size, count)
+                assert (iv.start_index, iv.end_index) == co.interval_by_rank(rank, size, count)
+    iv = bsr.interval_by_rank(3, 4, 5)                   # start 6 > end 5
+    assert iv.get_count() == (5 - 6) % (1 << 64)         # release-build wrap (load_balance.rs:14-16)
+    assert iv.rows(5) == (5, 0)                          # polars' clamping slice selects nothing
+    assert bsr.interval_by_rank(7, 8, 100_000_000).rows(100_000_000) == (87_500_000, 12_500_000)
+
+
+def test_slice_by_rank():
+    arr = list(range(10))
+    parts = [bsr.slice_by_rank(r, 4, arr).slice for r in range(4)]
+    assert parts == [[0, 1, 2], [3, 4, 5], [6, 7, 8], [9]]
+    with pytest.raises(IndexError):                      # Rust would panic on arr[6..5]
+        bsr.slice_by_rank(3, 4, list(range(5)))
+
+
+def test_candidate_keys_order_like_the_reference_sort():
+    rng = np.random.default_rng(0)
+    dist = rng.uniform(0, 2, 500).astype(F)
+    dist[10:20] = dist[10]                               # ties
+    dist[30] = 0.0
+    dist[31] = -0.0
+    idx = rng.permutation(500).astype(np.uint64)
+    keys = S.pack_candidates(idx, dist, 512)
+    order = np.argsort(keys[:500], kind="stable")
+    want = sorted(range(500), key=lambda i: (float(dist[i]), int(idx[i])))
+    assert order.tolist() == want
+    gi, gd = S.unpack_candidates(np.sort(keys), 500)
+    assert gi.tolist() == [int(idx[i]) for i in want]
+    assert np.array_equal(gd, np.abs(dist[want]))        # -0.0 canonicalised to +0.0
+    assert np.all(keys[500:] == S.KEY_MAX)
+    assert S.unpack_candidates(keys[500:], 12)[0].size == 0
+
+
+def test_candidate_slots():
+    assert [bsr.candidate_slots(k) for k in (1, 10, 32, 33, 100, 1024)] == [32, 32, 32, 64, 128, 1024]
+    for bad in (0, 1025, -1):
+        with pytest.raises(bsr.BsrError):
+            bsr.candidate_slots(bad)
+
+
+def test_accuracy_metrics_and_printing(capsys):
+    top = [(0, 0.0), (60, 0.8749089), (1230, 0.88296163)]
+    assert bsr.calculate_accuracy_metrics(top, 0, 50) == (1.0, 1.0, 1.0)
+    assert bsr.calculate_accuracy_metrics(top, 1230, 50) == co.calculate_accuracy_metrics([0, 60, 1230], 1230, 50)
+    assert bsr.calculate_accuracy_metrics(top, 1230, 2) == (pytest.approx(1 / 3), 0.0, 1.0)
+    assert bsr.calculate_accuracy_metrics(top, 99, 50) == (0.0, 0.0, 0.0)
+    bsr.print_top_k_results(top)
+    out = capsys.readouterr().out.splitlines()
+    assert out[0] == "Global top-3 results:"
+    assert out[1] == "  1. Index: 0, Distance: 0"
+    assert out[2] == "  2. Index: 60, Distance: 0.8749089"
+    assert bsr.format_accuracy_metrics(1.0, 1.0, 1.0, 50).splitlines()[2] == "  Recall@50: 1.0000"
+
+
+def test_parquet_helpers_roundtrip(tmp_path):
+    rows = co.generate_rows(3, 0, 123, 768)
+    p = str(tmp_path / "sub" / "global.parquet")
+    os.makedirs(os.path.dirname(p))
+    V._write_parquet_rows(p, rows)
+    back = V._read_parquet_rows(p)
+    assert back.dtype == F and np.array_equal(back.view(np.uint32), rows.view(np.uint32))
+    # a plain list<float> column (what another writer might produce) decodes the same
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    p2 = str(tmp_path / "plain.parquet")
+    pq.write_table(pa.table({"embeddings": pa.array(rows.tolist(), type=pa.list_(pa.float32()))}), p2)
+    assert np.array_equal(V._read_parquet_rows(p2), rows)
+    # a missing file is created empty, as read_parquet does (polars.rs:64-73)
+    p3 = str(tmp_path / "new" / "rank_0.parquet")
+    assert V._read_parquet_rows(p3).shape[0] == 0 and os.path.exists(p3)
+
+
+def test_store_paths():
+    # src/mpi_helpers/vectorstore.rs:5-20 naming contract, checked without opening a device
+    import inspect
+    assert 'f"rank_{rank}.parquet"' in inspect.getsource(bsr.get_local_vstore)
+    assert '"global.parquet"' in inspect.getsource(bsr.get_global_vstore)
