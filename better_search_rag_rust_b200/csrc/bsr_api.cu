@@ -70,7 +70,7 @@ struct bsr_store {
     size_t smem_optin = 0;
 
     // per-search scratch (grown on demand)
-    DevBuf cta_keys, merge_a, merge_b, d_queries, d_cand, d_idx, d_dist, d_count, staging;
+    DevBuf cta_keys, merge_a, merge_b, d_queries, d_cand, d_result, d_counter, staging;
     void* h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
 
@@ -222,7 +222,7 @@ extern "C" int bsr_store_destroy(bsr_store* s) {
     DeviceGuard g(s->device);
     cudaStreamSynchronize(s->stream);
     DevBuf* bufs[] = {&s->cta_keys, &s->merge_a, &s->merge_b, &s->d_queries,
-                      &s->d_cand,   &s->d_idx,   &s->d_dist,  &s->d_count,   &s->staging};
+                      &s->d_cand,   &s->d_result, &s->d_counter, &s->staging};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (s->panels) cudaFree(s->panels);
@@ -402,8 +402,10 @@ template <int U>
 static int launch_scan(bsr_store* s, const ScanArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
     static thread_local size_t configured[64] = {0};  // per device
     if (smem > 48 * 1024 && configured[s->device & 63] < smem) {
+        cudaFuncAttributes fa;
+        CU(cudaFuncGetAttributes(&fa, scan_topk_f32_kernel<U>));
         CU(cudaFuncSetAttribute(scan_topk_f32_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)s->smem_optin));
+                                (int)(s->smem_optin - fa.sharedSizeBytes)));
         configured[s->device & 63] = s->smem_optin;
     }
     scan_topk_f32_kernel<U><<<grid, kScanThreads, smem, st>>>(a);
@@ -465,7 +467,7 @@ static u32 bulk_stages(const bsr_store* s, u32 K) {
     // lose bandwidth: 6 stages -7 %); BSR_BULK_STAGES overrides for tuning.
     u32 st = 3;
     if (const char* e = getenv("BSR_BULK_STAGES")) st = std::max(2, atoi(e));
-    while (st >= 2 && bulk_smem_bytes(s, K, st) > s->smem_optin) st--;
+    while (st >= 2 && bulk_smem_bytes(s, K, st) + 1024 > s->smem_optin) st--;
     return st;  // < 2: does not fit
 }
 
@@ -473,8 +475,10 @@ static int launch_scan_bulk(bsr_store* s, const ScanArgs& a, unsigned grid, u32 
                             cudaStream_t st) {
     static thread_local bool configured[64] = {false};
     if (!configured[s->device & 63]) {
+        cudaFuncAttributes fa;
+        CU(cudaFuncGetAttributes(&fa, scan_topk_f32_bulk_kernel));
         CU(cudaFuncSetAttribute(scan_topk_f32_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)s->smem_optin));
+                                (int)(s->smem_optin - fa.sharedSizeBytes)));
         configured[s->device & 63] = true;
     }
     BulkScanArgs ba;
@@ -522,18 +526,26 @@ static unsigned scan_grid(const bsr_store* s, u32 n_panels, int warps_per_cta) {
     return std::max(1u, std::min<unsigned>((unsigned)s->n_sm, need));
 }
 
+// Scan + merge for nq queries.  Always writes the merged candidates to d_cand[nq][K]; when d_idx
+// is non-null also the unpacked idx[nq][k], dist[nq][k], count[nq].
 static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 k, u64* d_cand,
-                              cudaStream_t st) {
+                              u64* d_idx, float* d_dist, u32* d_count, cudaStream_t st) {
     const u32 K = bsr_candidate_slots(k);
     const u32 n_panels = (u32)((s->n_rows + 31) / 32);
     const u32 stages = bulk_stages(s, K);
     const bool bulk = scan_variant() == 1 && stages >= 2;
     const unsigned grid = scan_grid(s, n_panels, bulk ? kBulkWarps : kScanWarps);
     const size_t smem = (size_t)s->dq * sizeof(float4) + (size_t)kScanWarps * K * sizeof(u64);
-    CHECK(bulk || smem <= s->smem_optin, BSR_ERR_UNSUPPORTED,
+    CHECK(bulk || smem + 1024 <= s->smem_optin, BSR_ERR_UNSUPPORTED,
           "search: dim %u with top_k %u needs %zu bytes of shared memory (limit %zu)", s->dim, k,
           smem, s->smem_optin);
     TRY(ensure(s->cta_keys, (size_t)nq * grid * K * sizeof(u64)));
+    // k <= 32: the scan's last CTA merges the per-CTA lists and unpacks -> one kernel per query
+    const bool fuse = (K == 32);
+    if (!s->d_counter.p) {
+        TRY(ensure(s->d_counter, 256));
+        CU(cudaMemsetAsync(s->d_counter.p, 0, 256, st));
+    }
     const u32 max_per_cta = std::max<u32>(2, kMergeMaxKeys / K);
     const size_t inter = (size_t)nq * ((grid + max_per_cta - 1) / max_per_cta) * K * sizeof(u64);
     TRY(ensure(s->merge_a, inter));
@@ -553,6 +565,12 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
         a.k = k;
         a.k_pad = K;
         a.row_base = (u32)s->row_base;
+        a.fuse_final = fuse ? 1u : 0u;
+        a.fin.done_counter = (u32*)s->d_counter.p;
+        a.fin.keys = d_cand + (size_t)q * K;
+        a.fin.idx = d_idx ? d_idx + (size_t)q * k : nullptr;
+        a.fin.dist = d_idx ? d_dist + (size_t)q * k : nullptr;
+        a.fin.count = d_idx ? d_count + q : nullptr;
         TRY(prof_begin(s, st));
         if (bulk) TRY(launch_scan_bulk(s, a, grid, stages, st));
         else if (s->dq % 16 == 0 && getenv("BSR_LDG_U") && atoi(getenv("BSR_LDG_U")) == 16)
@@ -566,7 +584,14 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
     }
     CU(cudaEventRecord(s->ev_scan1, st));
     s->scan_timed = true;
-    return merge_tree(s, (const u64*)s->cta_keys.p, grid, nq, K, K, (size_t)grid * K, d_cand, st);
+    if (fuse) return BSR_OK;
+    TRY(merge_tree(s, (const u64*)s->cta_keys.p, grid, nq, K, K, (size_t)grid * K, d_cand, st));
+    if (d_idx) {
+        unpack_kernel<<<nq, 128, 0, st>>>(d_cand, K, k, d_idx, d_dist, d_count);
+        s->launches++;
+        CU(cudaGetLastError());
+    }
+    return BSR_OK;
 }
 
 static int check_search_args(const bsr_store* s, const void* q, u32 nq, u32 k, const char* fn) {
@@ -584,7 +609,7 @@ extern "C" int bsr_search_device(bsr_store* s, const float* d_queries, uint32_t 
     CHECK(d_candidates, BSR_ERR_INVALID, "bsr_search_device: null output");
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
-    return search_device_impl(s, d_queries, nq, k, (u64*)d_candidates, st);
+    return search_device_impl(s, d_queries, nq, k, (u64*)d_candidates, nullptr, nullptr, nullptr, st);
 }
 
 extern "C" int bsr_merge_device(bsr_store* s, const uint64_t* d_lists, uint32_t n_lists,
@@ -627,35 +652,30 @@ extern "C" int bsr_search(bsr_store* s, const float* queries, uint32_t nq, uint3
     const size_t qbytes = (size_t)nq * s->dim * sizeof(float);
     const size_t ibytes = (size_t)nq * k * sizeof(u64), dbytes = (size_t)nq * k * sizeof(float),
                  cbytes = (size_t)nq * sizeof(u32);
-    // pinned layout: [queries | idx | dist | count]
-    const size_t off_i = (qbytes + 15) & ~(size_t)15, off_d = off_i + ibytes, off_c = off_d + dbytes;
-    TRY(ensure_pinned(s, off_c + cbytes));
+    // one packed result block [idx | dist | count] on the device and in pinned host memory, so a
+    // search is one H2D copy, the kernels, one D2H copy
+    const size_t rbytes = ibytes + dbytes + cbytes;
+    const size_t off_r = (qbytes + 15) & ~(size_t)15;
+    TRY(ensure_pinned(s, off_r + rbytes));
     TRY(ensure(s->d_queries, qbytes));
     TRY(ensure(s->d_cand, (size_t)nq * K * sizeof(u64)));
-    TRY(ensure(s->d_idx, ibytes));
-    TRY(ensure(s->d_dist, dbytes));
-    TRY(ensure(s->d_count, cbytes));
+    TRY(ensure(s->d_result, rbytes));
     char* h = (char*)s->h_pinned;
     memcpy(h, queries, qbytes);
-    CU(cudaMemcpyAsync(s->d_queries.p, h, qbytes, cudaMemcpyHostToDevice, s->stream));
     if (s->n_rows == 0) {
         // empty shard: compute_local_top_k returns an empty list (metrics.rs:36-52)
-        CU(cudaStreamSynchronize(s->stream));
         memset(out_count, 0, cbytes);
         return BSR_OK;
     }
-    TRY(search_device_impl(s, (const float*)s->d_queries.p, nq, k, (u64*)s->d_cand.p, s->stream));
-    unpack_kernel<<<nq, 128, 0, s->stream>>>((const u64*)s->d_cand.p, K, k, (u64*)s->d_idx.p,
-                                             (float*)s->d_dist.p, (u32*)s->d_count.p);
-    s->launches++;
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(h + off_i, s->d_idx.p, ibytes, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(h + off_d, s->d_dist.p, dbytes, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(h + off_c, s->d_count.p, cbytes, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(s->d_queries.p, h, qbytes, cudaMemcpyHostToDevice, s->stream));
+    char* r = (char*)s->d_result.p;
+    TRY(search_device_impl(s, (const float*)s->d_queries.p, nq, k, (u64*)s->d_cand.p, (u64*)r,
+                           (float*)(r + ibytes), (u32*)(r + ibytes + dbytes), s->stream));
+    CU(cudaMemcpyAsync(h + off_r, r, rbytes, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
-    memcpy(out_idx, h + off_i, ibytes);
-    memcpy(out_dist, h + off_d, dbytes);
-    memcpy(out_count, h + off_c, cbytes);
+    memcpy(out_idx, h + off_r, ibytes);
+    memcpy(out_dist, h + off_r + ibytes, dbytes);
+    memcpy(out_count, h + off_r + ibytes + dbytes, cbytes);
     return BSR_OK;
 }
 

@@ -205,18 +205,20 @@ struct WarpTopK {
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cta_merge_lists(u64* buf, u32 L, u32 K) {
     const u32 tid = threadIdx.x, nt = blockDim.x;
+    const u32 logK = 31 - __clz(K);
     for (u32 s = L >> 1; s >= 1; s >>= 1) {
-        for (u32 t = tid; t < s * K; t += nt) {
-            const u32 i = t / K, j = t - i * K;
-            const u64 a = buf[i * K + j];
-            const u64 b = buf[(i + s) * K + (K - 1 - j)];
-            buf[i * K + j] = a < b ? a : b;
+        for (u32 t = tid; t < (s << logK); t += nt) {
+            const u32 i = t >> logK, j = t & (K - 1);
+            const u64 a = buf[(i << logK) + j];
+            const u64 b = buf[((i + s) << logK) + (K - 1 - j)];
+            buf[(i << logK) + j] = a < b ? a : b;
         }
         __syncthreads();
-        for (u32 d = K >> 1; d >= 1; d >>= 1) {
-            for (u32 t = tid; t < s * (K >> 1); t += nt) {
-                const u32 i = t / (K >> 1), jj = t - i * (K >> 1);
-                const u32 lo = i * K + ((jj / d) * 2 * d) + (jj % d);
+        for (u32 ld = logK; ld-- > 0;) {
+            const u32 d = 1u << ld;
+            for (u32 t = tid; t < (s << (logK - 1)); t += nt) {
+                const u32 i = t >> (logK - 1), jj = t & ((K >> 1) - 1);
+                const u32 lo = (i << logK) + ((jj >> ld) << (ld + 1)) + (jj & (d - 1));
                 const u32 hi = lo + d;
                 const u64 x = buf[lo], y = buf[hi];
                 if (x > y) {
@@ -226,6 +228,87 @@ __device__ __forceinline__ void cta_merge_lists(u64* buf, u32 L, u32 K) {
             }
             __syncthreads();
         }
+    }
+}
+
+// Register version for K == 32: lane i holds the i-th key of an ascending list.  Returns (lane i
+// of) the 32 smallest keys of the two lists, ascending: min(a[i], b[31-i]) is bitonic, five
+// shuffle half-cleaners sort it.
+__device__ __forceinline__ u64 warp_merge32(u64 mine, u64 other, int lane) {
+    const u64 rev = __shfl_sync(0xFFFFFFFFu, other, 31 - lane);
+    u64 v = mine < rev ? mine : rev;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const u64 p = __shfl_xor_sync(0xFFFFFFFFu, v, d);
+        const bool keep_min = (lane & d) == 0;
+        v = (keep_min == (v < p)) ? v : p;
+    }
+    return v;
+}
+
+__device__ __forceinline__ u64 ldcg_u64(const u64* p) {
+    u64 v;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+// Optional outputs of the fused final stage (see scan_epilogue)
+struct FinalOut {
+    u32* done_counter;  // zero before the launch; the last CTA to finish resets it
+    u64* keys;          // [k_pad] merged candidates of the whole shard
+    u64* idx;           // [k]  or nullptr
+    float* dist;        // [k]
+    u32* count;         // [1]
+};
+
+// End of a scan CTA: reduce the W per-warp lists in shared memory to the CTA's best K, publish
+// them, and -- when the launch fuses the final stage (K == 32) -- let the last CTA to finish merge
+// every CTA's list and unpack the result, so a whole search is one kernel.
+template <int W>
+__device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta_keys,
+                                              const FinalOut& fo, bool fuse_final) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ u32 s_is_last;
+    u64* mine = cta_keys + (size_t)blockIdx.x * K;
+    if (K == 32) {
+        if (warp == 0) {
+            u64 v = lists[lane];
+#pragma unroll
+            for (int w = 1; w < W; w++) v = warp_merge32(v, lists[w * 32 + lane], lane);
+            mine[lane] = v;
+        }
+    } else {
+        cta_merge_lists(lists, W, K);
+        for (u32 j = tid; j < K; j += W * 32) mine[j] = lists[j];
+    }
+    if (!fuse_final) return;
+
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_is_last = (atomicAdd(fo.done_counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_is_last) return;
+    __threadfence();
+    // K == 32: every warp folds a strided subset of the CTA lists in registers
+    u64 v = kKeyMax;
+    for (u32 l = warp; l < gridDim.x; l += W) v = warp_merge32(v, ldcg_u64(cta_keys + (size_t)l * 32 + lane), lane);
+    lists[warp * 32 + lane] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = lists[lane];
+#pragma unroll
+        for (int w = 1; w < W; w++) v = warp_merge32(v, lists[w * 32 + lane], lane);
+        fo.keys[lane] = v;
+        if (fo.idx) {
+            const bool ok = (u32)lane < k && v != kKeyMax;
+            if ((u32)lane < k) {
+                fo.idx[lane] = ok ? (v & 0xFFFFFFFFull) : 0ull;
+                fo.dist[lane] = ok ? __uint_as_float(bits_from_ordered((u32)(v >> 32))) : 0.0f;
+            }
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+            if (lane == 0) *fo.count = (u32)__popc(m);
+        }
+        if (lane == 0) *fo.done_counter = 0;
     }
 }
 
@@ -241,6 +324,8 @@ struct ScanArgs {
     u64* cta_keys;         // [gridDim.x][k_pad]
     u32 n_rows, n_panels, dq, dim, k, k_pad;
     u32 row_base;          // global index of local row 0
+    u32 fuse_final;        // 1: the last CTA also merges all CTA lists (requires k_pad == 32)
+    FinalOut fin;
 };
 
 template <int U>
@@ -335,9 +420,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_f32_kernel(const Sc
     }
     top.finish(lane);
     __syncthreads();
-    cta_merge_lists(lists, kScanWarps, a.k_pad);
-    u64* out = a.cta_keys + (size_t)blockIdx.x * a.k_pad;
-    for (u32 j = tid; j < a.k_pad; j += kScanThreads) out[j] = lists[j];
+    scan_epilogue<kScanWarps>(lists, a.k_pad, a.k, a.cta_keys, a.fin, a.fuse_final != 0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -514,9 +597,7 @@ __global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_f32_bulk_kernel(con
     }
     top.finish(lane);
     __syncthreads();
-    cta_merge_lists(lists, kBulkWarps, a.k_pad);
-    u64* out = a.cta_keys + (size_t)blockIdx.x * a.k_pad;
-    for (u32 j = tid; j < a.k_pad; j += kBulkThreads) out[j] = lists[j];
+    scan_epilogue<kBulkWarps>(lists, a.k_pad, a.k, a.cta_keys, a.fin, a.fuse_final != 0);
 }
 
 // ------------------------------------------------------------------------------------------
