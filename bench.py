@@ -431,10 +431,34 @@ def run_b200(args) -> None:
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    # The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, torchrun
+    # notices) also write to fd 1, so everything except that line is sent to stderr.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    line_holder = []
+    import builtins
+    orig_print = builtins.print
+
+    def capture_print(*a, **kw):
+        if kw.get("file") in (None, sys.stdout) and len(a) == 1 and isinstance(a[0], str) and a[0].startswith("{"):
+            line_holder.append(a[0])
+        else:
+            orig_print(*a, **kw)
+
+    builtins.print = capture_print
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_b200(args)
+    finally:
+        builtins.print = orig_print
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for line in line_holder:
+        print(line, flush=True)
 
 
 if __name__ == "__main__":

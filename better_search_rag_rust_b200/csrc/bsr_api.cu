@@ -679,6 +679,62 @@ extern "C" int bsr_search(bsr_store* s, const float* queries, uint32_t nq, uint3
     return BSR_OK;
 }
 
+extern "C" int bsr_merge_host(bsr_store* s, const uint64_t* idx, const float* dist, uint64_t n,
+                              uint32_t k, uint64_t* out_idx, float* out_dist, uint32_t* out_count) {
+    CHECK(s, BSR_ERR_INVALID, "bsr_merge_host: null store");
+    CHECK(k >= 1 && k <= BSR_MAX_TOP_K, BSR_ERR_INVALID, "bsr_merge_host: top_k %u outside [1, %u]", k,
+          BSR_MAX_TOP_K);
+    CHECK(out_count, BSR_ERR_INVALID, "bsr_merge_host: null output");
+    *out_count = 0;
+    if (n == 0) return BSR_OK;
+    CHECK(idx && dist && out_idx && out_dist, BSR_ERR_INVALID, "bsr_merge_host: null argument");
+    CHECK(n <= (1ull << 26), BSR_ERR_RANGE, "bsr_merge_host: too many candidates (%llu)",
+          (unsigned long long)n);
+    for (u64 i = 0; i < n; i++)
+        CHECK(idx[i] < 0xFFFFFFFFull, BSR_ERR_RANGE, "bsr_merge_host: index %llu does not fit 32 bits",
+              (unsigned long long)idx[i]);
+    DeviceGuard g(s->device);
+    const u32 K = bsr_candidate_slots(k);
+    const u32 n_lists = (u32)((n + K - 1) / K);
+    const size_t in_bytes = (size_t)n * (sizeof(u64) + sizeof(float));
+    const size_t ibytes = (size_t)k * sizeof(u64), dbytes = (size_t)k * sizeof(float);
+    const size_t rbytes = ibytes + dbytes + sizeof(u32);
+    TRY(ensure_pinned(s, std::max(in_bytes, rbytes)));
+    TRY(ensure(s->staging, in_bytes));
+    TRY(ensure(s->cta_keys, (size_t)n_lists * K * sizeof(u64)));
+    TRY(ensure(s->d_cand, (size_t)K * sizeof(u64)));
+    TRY(ensure(s->d_result, rbytes));
+    const u32 max_per_cta = std::max<u32>(2, kMergeMaxKeys / K);
+    const size_t inter = (size_t)((n_lists + max_per_cta - 1) / max_per_cta) * K * sizeof(u64);
+    TRY(ensure(s->merge_a, inter));
+    TRY(ensure(s->merge_b, inter));
+    char* h = (char*)s->h_pinned;
+    memcpy(h, idx, (size_t)n * sizeof(u64));
+    memcpy(h + (size_t)n * sizeof(u64), dist, (size_t)n * sizeof(float));
+    CU(cudaMemcpyAsync(s->staging.p, h, in_bytes, cudaMemcpyHostToDevice, s->stream));
+    const u64* d_i = (const u64*)s->staging.p;
+    const float* d_d = (const float*)((char*)s->staging.p + (size_t)n * sizeof(u64));
+    pack_sort_lists_kernel<<<n_lists, 256, (size_t)K * sizeof(u64), s->stream>>>(d_i, d_d, n, K,
+                                                                                 (u64*)s->cta_keys.p);
+    s->launches++;
+    CU(cudaGetLastError());
+    TRY(merge_tree(s, (const u64*)s->cta_keys.p, n_lists, 1, K, K, (size_t)n_lists * K,
+                   (u64*)s->d_cand.p, s->stream));
+    char* r = (char*)s->d_result.p;
+    unpack_kernel<<<1, 128, 0, s->stream>>>((const u64*)s->d_cand.p, K, k, (u64*)r, (float*)(r + ibytes),
+                                            (u32*)(r + ibytes + dbytes));
+    s->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h, r, rbytes, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    u32 cnt;
+    memcpy(&cnt, h + ibytes + dbytes, sizeof(u32));
+    memcpy(out_idx, h, (size_t)cnt * sizeof(u64));
+    memcpy(out_dist, h + ibytes, (size_t)cnt * sizeof(float));
+    *out_count = cnt;
+    return BSR_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // introspection
 // ---------------------------------------------------------------------------------------------

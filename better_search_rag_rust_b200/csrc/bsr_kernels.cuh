@@ -625,6 +625,35 @@ __global__ void __launch_bounds__(kMergeThreads) merge_lists_kernel(
     for (u32 j = threadIdx.x; j < K; j += blockDim.x) o[j] = buf[j];
 }
 
+// (idx, dist) pairs -> candidate keys, cut into lists of K slots; a list must be ascending for the
+// merge, so each list is sorted here by one CTA (bitonic, K <= 1024 keys in shared memory).
+__global__ void pack_sort_lists_kernel(const u64* __restrict__ idx, const float* __restrict__ dist,
+                                       u64 n, u32 K, u64* __restrict__ lists) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    u64* buf = reinterpret_cast<u64*>(smem_raw);
+    const u64 base = (u64)blockIdx.x * K;
+    for (u32 j = threadIdx.x; j < K; j += blockDim.x) {
+        const u64 i = base + j;
+        buf[j] = (i < n) ? make_key(dist[i], (u32)idx[i]) : kKeyMax;
+    }
+    __syncthreads();
+    for (u32 size = 2; size <= K; size <<= 1) {
+        for (u32 d = size >> 1; d >= 1; d >>= 1) {
+            for (u32 t = threadIdx.x; t < (K >> 1); t += blockDim.x) {
+                const u32 lo = ((t / d) * 2 * d) + (t % d), hi = lo + d;
+                const bool asc = (lo & size) == 0;
+                const u64 x = buf[lo], y = buf[hi];
+                if ((x > y) == asc) {
+                    buf[lo] = y;
+                    buf[hi] = x;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (u32 j = threadIdx.x; j < K; j += blockDim.x) lists[base + j] = buf[j];
+}
+
 // candidates[q][K] -> idx[q][k] (u64, as the reference's usize), dist[q][k], count[q]
 __global__ void unpack_kernel(const u64* __restrict__ cand, u32 K, u32 k, u64* __restrict__ idx,
                               float* __restrict__ dist, u32* __restrict__ count) {

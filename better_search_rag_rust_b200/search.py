@@ -301,32 +301,36 @@ def compute_global_top_k(global_indices: Sequence[int], global_distances: Sequen
                          top_k: int, *, device: Optional[int] = None, engine=None) -> TopK:
     """metrics.rs:141-171: sort the gathered candidates on the GPU and keep the first top_k.
 
-    Candidates are packed `slots` at a time into lists for bsr_merge_device; indices are unique
-    (disjoint row blocks), which makes the reference's HashSet pass (:156-168) a no-op."""
-    import torch
-    gi = np.asarray(global_indices, dtype=np.uint64).ravel()
-    gd = np.asarray(global_distances, dtype=np.float32).ravel()
+    One bsr_merge_host call: H2D of the pairs, key packing + per-list sort, merge tree, unpack,
+    D2H.  Indices are unique (disjoint row blocks), which makes the reference's HashSet pass
+    (:156-168) a no-op."""
+    gi = np.ascontiguousarray(global_indices, dtype=np.uint64).ravel()
+    gd = np.ascontiguousarray(global_distances, dtype=np.float32).ravel()
     if gi.size != gd.size:
         raise ValueError("global_indices and global_distances differ in length")
     if gi.size == 0:
         return []
     eng = engine or _merge_engine(_default_device(0) if device is None else device)
+    if not hasattr(eng, "store"):  # test double
+        cand = eng.merge(_torch_keys(gi, gd, top_k), top_k)
+        idx, dist, count = eng.unpack(cand, top_k)
+        return _pairs(idx[0], dist[0], count[0])
+    idx = np.zeros(top_k, dtype=np.uint64)
+    dist = np.zeros(top_k, dtype=np.float32)
+    count = C.c_uint32()
+    _lib.check(_lib.lib().bsr_merge_host(eng.store.handle, gi.ctypes.data, gd.ctypes.data, gi.size,
+                                         top_k, idx.ctypes.data, dist.ctypes.data, C.byref(count)))
+    return _pairs(idx, dist, count.value)
+
+
+def _torch_keys(gi, gd, top_k):
+    import torch
     slots = candidate_slots(top_k)
-    # the merge kernel wants ascending lists: cut the input into runs that are already ascending
-    # by key (each rank's list is), then pad every run to `slots`
-    keys = pack_candidates(gi, gd, gi.size)
-    cuts = [0] + [i for i in range(1, keys.size) if keys[i] < keys[i - 1]] + [keys.size]
-    runs = []
-    for a, b in zip(cuts[:-1], cuts[1:]):
-        for s in range(a, b, slots):
-            run = np.full(slots, KEY_MAX, dtype=np.uint64)
-            seg = keys[s:min(b, s + slots)]
-            run[:seg.size] = seg
-            runs.append(run)
-    lists = torch.from_numpy(np.stack(runs).view(np.int64)).reshape(len(runs), 1, slots)
-    merged = eng.merge(lists, top_k)
-    idx, dist, count = eng.unpack(merged, top_k)
-    return _pairs(idx[0], dist[0], count[0])
+    n_lists = -(-gi.size // slots)
+    keys = np.full(n_lists * slots, KEY_MAX, dtype=np.uint64)
+    keys[:gi.size] = pack_candidates(gi, gd, gi.size)
+    keys = np.sort(keys.reshape(n_lists, slots), axis=1)
+    return torch.from_numpy(keys.view(np.int64)).reshape(n_lists, 1, slots)
 
 
 def parallel_top_k_similarity_search(world, rank: int, size: int, vstore_dir, top_k: int,

@@ -152,6 +152,13 @@ BSR_API int bsr_unpack_device(bsr_store *store, const uint64_t *d_candidates, ui
                       uint32_t top_k, uint64_t *d_idx, float *d_dist, uint32_t *d_count,
                       void *stream);
 
+/* compute_global_top_k (metrics.rs:141-171) with host buffers: the n gathered (index, distance)
+ * pairs -- the rank-ordered concatenation gather_top_k_results builds at root -- are sorted on the
+ * device by (distance, index) and the first min(top_k, n) written to out_idx/out_dist; *out_count
+ * receives how many.  Indices must be < 2^32 - 1. */
+BSR_API int bsr_merge_host(bsr_store *store, const uint64_t *idx, const float *dist, uint64_t n,
+                           uint32_t top_k, uint64_t *out_idx, float *out_dist, uint32_t *out_count);
+
 /* ---- introspection for the benchmark harness ---------------------------------------------- */
 
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */

@@ -1,0 +1,76 @@
+"""GPU, >= 2 devices: parallel_top_k_similarity_search over NCCL (one process per GPU) against the
+oracle's parallel search.  Skipped on a single-GPU box; the single-GPU suite covers the same
+pipeline with shards run back to back (tests/test_gpu_parity.py::_sharded_search)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, size, port, n_rows, k, q_out):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=size, device_id=torch.device("cuda", rank))
+    try:
+        import better_search_rag_rust_b200 as bsr
+        seed = 0x5EED0001
+        iv = bsr.interval_by_rank(rank, size, n_rows)
+        first, cnt = iv.rows(n_rows)
+        store = bsr.GpuVectorstore(None, True, device=rank, dim=768, row_base=iv.start_index)
+        store.append_synthetic(seed, first, cnt)
+        eng = bsr.CudaShardEngine(store)
+        q = torch.zeros(768, device="cuda")
+        if rank == 0:
+            q.copy_(torch.from_numpy(store.get(0)))
+        dist.broadcast(q, src=0)                       # src/main.rs:123-125
+        out = []
+        for query in (q.cpu().numpy(), np.linspace(-1, 1, 768, dtype=np.float32)):
+            out.append(bsr.parallel_top_k_similarity_search(None, rank, size, None, k, query, engine=eng))
+        q_out.put((rank, out))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("k", [10, 100])
+def test_nccl_parallel_search(k):
+    import torch
+    import torch.multiprocessing as mp
+    from oracle import c_oracle as co
+    size = min(torch.cuda.device_count(), 4)
+    if size < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n_rows = 100_003
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, size, port, n_rows, k, q)) for r in range(size)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(size))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    rows = co.generate_rows(0x5EED0001, 0, n_rows, 768)
+    for qi, query in enumerate((rows[0], np.linspace(-1, 1, 768, dtype=np.float32))):
+        wi, wd = co.parallel_top_k_similarity_search(rows, size, k, query, n_threads=8)
+        got = res[0][qi]
+        assert [p[0] for p in got] == wi.tolist()
+        assert np.asarray([p[1] for p in got], np.float32).view(np.uint32).tolist() == wd.view(np.uint32).tolist()
+        for r in range(1, size):
+            assert res[r][qi] is None
