@@ -457,34 +457,45 @@ static int scan_variant() {
     return v;
 }
 
-static size_t bulk_smem_bytes(const bsr_store* s, u32 K, u32 stages) {
-    return (size_t)kBulkWarps * stages * kChunkBytes + (size_t)s->dq * sizeof(float4) +
-           (size_t)kBulkWarps * K * sizeof(u64) + (size_t)kBulkWarps * stages * sizeof(u64);
+static size_t bulk_smem_bytes(const bsr_store* s, u32 K, u32 stages, u32 qb) {
+    return (size_t)kBulkWarps * stages * kChunkBytes + (size_t)qb * s->dq * sizeof(float4) +
+           (size_t)qb * kBulkWarps * K * sizeof(u64) + (size_t)kBulkWarps * stages * sizeof(u64);
 }
 
-static u32 bulk_stages(const bsr_store* s, u32 K) {
+static u32 bulk_stages(const bsr_store* s, u32 K, u32 qb) {
     // 3 stages x 4 KiB x 8 warps = 96 KiB in flight per SM measured fastest on B200 (deeper rings
     // lose bandwidth: 6 stages -7 %); BSR_BULK_STAGES overrides for tuning.
     u32 st = 3;
     if (const char* e = getenv("BSR_BULK_STAGES")) st = std::max(2, atoi(e));
-    while (st >= 2 && bulk_smem_bytes(s, K, st) + 1024 > s->smem_optin) st--;
+    while (st >= 2 && bulk_smem_bytes(s, K, st, qb) + 1024 > s->smem_optin) st--;
     return st;  // < 2: does not fit
 }
 
+// largest query-batch width (8, 4, 2, 1) whose lists fit next to a >= 2-stage ring
+static u32 bulk_max_qb(const bsr_store* s, u32 K) {
+    u32 cap = 8;
+    if (const char* e = getenv("BSR_MAX_QB")) cap = std::max(1, atoi(e));
+    for (u32 qb = 8; qb >= 2; qb >>= 1)
+        if (qb <= cap && bulk_stages(s, K, qb) >= 2) return qb;
+    return 1;
+}
+
+template <int QB>
 static int launch_scan_bulk(bsr_store* s, const ScanArgs& a, unsigned grid, u32 stages,
                             cudaStream_t st) {
     static thread_local bool configured[64] = {false};
     if (!configured[s->device & 63]) {
         cudaFuncAttributes fa;
-        CU(cudaFuncGetAttributes(&fa, scan_topk_f32_bulk_kernel));
-        CU(cudaFuncSetAttribute(scan_topk_f32_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CU(cudaFuncGetAttributes(&fa, scan_topk_f32_bulk_kernel<QB>));
+        CU(cudaFuncSetAttribute(scan_topk_f32_bulk_kernel<QB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(s->smem_optin - fa.sharedSizeBytes)));
         configured[s->device & 63] = true;
     }
     BulkScanArgs ba;
     ba.s = a;
     ba.stages = stages;
-    scan_topk_f32_bulk_kernel<<<grid, kBulkThreads, bulk_smem_bytes(s, a.k_pad, stages), st>>>(ba);
+    scan_topk_f32_bulk_kernel<QB>
+        <<<grid, kBulkThreads, bulk_smem_bytes(s, a.k_pad, stages, QB), st>>>(ba);
     s->launches++;
     CU(cudaGetLastError());
     return BSR_OK;
@@ -532,15 +543,14 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
                               u64* d_idx, float* d_dist, u32* d_count, cudaStream_t st) {
     const u32 K = bsr_candidate_slots(k);
     const u32 n_panels = (u32)((s->n_rows + 31) / 32);
-    const u32 stages = bulk_stages(s, K);
-    const bool bulk = scan_variant() == 1 && stages >= 2;
+    const bool bulk = scan_variant() == 1 && bulk_stages(s, K, 1) >= 2;
     const unsigned grid = scan_grid(s, n_panels, bulk ? kBulkWarps : kScanWarps);
     const size_t smem = (size_t)s->dq * sizeof(float4) + (size_t)kScanWarps * K * sizeof(u64);
     CHECK(bulk || smem + 1024 <= s->smem_optin, BSR_ERR_UNSUPPORTED,
           "search: dim %u with top_k %u needs %zu bytes of shared memory (limit %zu)", s->dim, k,
           smem, s->smem_optin);
     TRY(ensure(s->cta_keys, (size_t)nq * grid * K * sizeof(u64)));
-    // k <= 32: the scan's last CTA merges the per-CTA lists and unpacks -> one kernel per query
+    // k <= 32: the scan's last CTA merges the per-CTA lists and unpacks -> one kernel per launch
     const bool fuse = (K == 32);
     if (!s->d_counter.p) {
         TRY(ensure(s->d_counter, 256));
@@ -550,9 +560,13 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
     const size_t inter = (size_t)nq * ((grid + max_per_cta - 1) / max_per_cta) * K * sizeof(u64);
     TRY(ensure(s->merge_a, inter));
     TRY(ensure(s->merge_b, inter));
+    const u32 max_qb = bulk ? bulk_max_qb(s, K) : 1;
 
     CU(cudaEventRecord(s->ev_scan0, st));
-    for (u32 q = 0; q < nq; q++) {
+    for (u32 q = 0; q < nq;) {
+        // queries are scanned in groups that share one pass over the store
+        u32 qb = max_qb;
+        while (qb > nq - q) qb >>= 1;
         ScanArgs a;
         a.panels = s->panels;
         a.norms = s->norms;
@@ -572,8 +586,13 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
         a.fin.dist = d_idx ? d_dist + (size_t)q * k : nullptr;
         a.fin.count = d_idx ? d_count + q : nullptr;
         TRY(prof_begin(s, st));
-        if (bulk) TRY(launch_scan_bulk(s, a, grid, stages, st));
-        else if (s->dq % 16 == 0 && getenv("BSR_LDG_U") && atoi(getenv("BSR_LDG_U")) == 16)
+        if (bulk) {
+            const u32 stages = bulk_stages(s, K, qb);
+            if (qb == 8) TRY(launch_scan_bulk<8>(s, a, grid, stages, st));
+            else if (qb == 4) TRY(launch_scan_bulk<4>(s, a, grid, stages, st));
+            else if (qb == 2) TRY(launch_scan_bulk<2>(s, a, grid, stages, st));
+            else TRY(launch_scan_bulk<1>(s, a, grid, stages, st));
+        } else if (s->dq % 16 == 0 && getenv("BSR_LDG_U") && atoi(getenv("BSR_LDG_U")) == 16)
             TRY(launch_scan<16>(s, a, grid, smem, st));
         else if (s->dq % 8 == 0 && !(getenv("BSR_LDG_U") && atoi(getenv("BSR_LDG_U")) == 4))
             TRY(launch_scan<8>(s, a, grid, smem, st));
@@ -581,6 +600,7 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
         else if (s->dq % 2 == 0) TRY(launch_scan<2>(s, a, grid, smem, st));
         else TRY(launch_scan<1>(s, a, grid, smem, st));
         TRY(prof_end(s, st));
+        q += qb;
     }
     CU(cudaEventRecord(s->ev_scan1, st));
     s->scan_timed = true;

@@ -252,34 +252,39 @@ __device__ __forceinline__ u64 ldcg_u64(const u64* p) {
     return v;
 }
 
-// Optional outputs of the fused final stage (see scan_epilogue)
+// Optional outputs of the fused final stage (see scan_epilogue); all indexed by query
 struct FinalOut {
     u32* done_counter;  // zero before the launch; the last CTA to finish resets it
-    u64* keys;          // [k_pad] merged candidates of the whole shard
-    u64* idx;           // [k]  or nullptr
-    float* dist;        // [k]
-    u32* count;         // [1]
+    u64* keys;          // [nq][k_pad] merged candidates of the whole shard
+    u64* idx;           // [nq][k]  or nullptr
+    float* dist;        // [nq][k]
+    u32* count;         // [nq]
 };
 
-// End of a scan CTA: reduce the W per-warp lists in shared memory to the CTA's best K, publish
-// them, and -- when the launch fuses the final stage (K == 32) -- let the last CTA to finish merge
-// every CTA's list and unpack the result, so a whole search is one kernel.
-template <int W>
+// End of a scan CTA that handled NQ queries: for each query reduce the W per-warp lists
+// (lists[q][w][K] in shared memory) to the CTA's best K and publish them to
+// cta_keys[q][cta][K]; when the launch fuses the final stage (K == 32) the last CTA to finish
+// merges every CTA's list and unpacks the result, so a whole search is one kernel.
+template <int W, int NQ>
 __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta_keys,
                                               const FinalOut& fo, bool fuse_final) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ u32 s_is_last;
-    u64* mine = cta_keys + (size_t)blockIdx.x * K;
+    const size_t q_stride = (size_t)gridDim.x * K;  // between queries in cta_keys
     if (K == 32) {
-        if (warp == 0) {
-            u64 v = lists[lane];
+        // warp w reduces queries w, w+W, ... entirely in registers
+        for (int q = warp; q < NQ; q += W) {
+            u64 v = lists[((size_t)q * W) * 32 + lane];
 #pragma unroll
-            for (int w = 1; w < W; w++) v = warp_merge32(v, lists[w * 32 + lane], lane);
-            mine[lane] = v;
+            for (int w = 1; w < W; w++) v = warp_merge32(v, lists[((size_t)q * W + w) * 32 + lane], lane);
+            cta_keys[q * q_stride + (size_t)blockIdx.x * 32 + lane] = v;
         }
     } else {
-        cta_merge_lists(lists, W, K);
-        for (u32 j = tid; j < K; j += W * 32) mine[j] = lists[j];
+        for (int q = 0; q < NQ; q++) {
+            u64* ql = lists + (size_t)q * W * K;
+            cta_merge_lists(ql, W, K);
+            for (u32 j = tid; j < K; j += W * 32) cta_keys[q * q_stride + (size_t)blockIdx.x * K + j] = ql[j];
+        }
     }
     if (!fuse_final) return;
 
@@ -289,27 +294,30 @@ __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta
     __syncthreads();
     if (!s_is_last) return;
     __threadfence();
-    // K == 32: every warp folds a strided subset of the CTA lists in registers
-    u64 v = kKeyMax;
-    for (u32 l = warp; l < gridDim.x; l += W) v = warp_merge32(v, ldcg_u64(cta_keys + (size_t)l * 32 + lane), lane);
-    lists[warp * 32 + lane] = v;
+    // K == 32: every warp folds a strided subset of the CTA lists in registers, per query
+    for (int q = 0; q < NQ; q++) {
+        u64 v = kKeyMax;
+        const u64* src = cta_keys + q * q_stride;
+        for (u32 l = warp; l < gridDim.x; l += W) v = warp_merge32(v, ldcg_u64(src + (size_t)l * 32 + lane), lane);
+        lists[((size_t)q * W + warp) * 32 + lane] = v;
+    }
     __syncthreads();
-    if (warp == 0) {
-        v = lists[lane];
+    for (int q = warp; q < NQ; q += W) {
+        u64 v = lists[((size_t)q * W) * 32 + lane];
 #pragma unroll
-        for (int w = 1; w < W; w++) v = warp_merge32(v, lists[w * 32 + lane], lane);
-        fo.keys[lane] = v;
+        for (int w = 1; w < W; w++) v = warp_merge32(v, lists[((size_t)q * W + w) * 32 + lane], lane);
+        fo.keys[(size_t)q * 32 + lane] = v;
         if (fo.idx) {
             const bool ok = (u32)lane < k && v != kKeyMax;
             if ((u32)lane < k) {
-                fo.idx[lane] = ok ? (v & 0xFFFFFFFFull) : 0ull;
-                fo.dist[lane] = ok ? __uint_as_float(bits_from_ordered((u32)(v >> 32))) : 0.0f;
+                fo.idx[(size_t)q * k + lane] = ok ? (v & 0xFFFFFFFFull) : 0ull;
+                fo.dist[(size_t)q * k + lane] = ok ? __uint_as_float(bits_from_ordered((u32)(v >> 32))) : 0.0f;
             }
             const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
-            if (lane == 0) *fo.count = (u32)__popc(m);
+            if (lane == 0) fo.count[q] = (u32)__popc(m);
         }
-        if (lane == 0) *fo.done_counter = 0;
     }
+    if (tid == 0) *fo.done_counter = 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -420,7 +428,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_f32_kernel(const Sc
     }
     top.finish(lane);
     __syncthreads();
-    scan_epilogue<kScanWarps>(lists, a.k_pad, a.k, a.cta_keys, a.fin, a.fuse_final != 0);
+    scan_epilogue<kScanWarps, 1>(lists, a.k_pad, a.k, a.cta_keys, a.fin, a.fuse_final != 0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -479,16 +487,19 @@ struct BulkScanArgs {
     u32 stages;  // ring depth per warp (>= 2)
 };
 
+// QB queries share one pass over the store: the row chunk is read from shared memory once and
+// feeds QB independent sequential dot products (a.query -> [QB][dim], outputs indexed by query).
+template <int QB>
 __global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_f32_bulk_kernel(const BulkScanArgs ba) {
     const ScanArgs& a = ba.s;
     constexpr int CH = kChunkQuads;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const u32 dq = a.dq, S = ba.stages;
-    // [ring: W*S*4KiB | query: dq*16 | lists: W*K*8 | mbarriers: W*S*8]
+    const u32 dq = a.dq, S = ba.stages, K = a.k_pad;
+    // [ring: W*S*4KiB | queries: QB*dq*16 | lists: QB*W*K*8 | mbarriers: W*S*8]
     unsigned char* ring_all = smem_raw;
     float4* sq = reinterpret_cast<float4*>(ring_all + (size_t)kBulkWarps * S * kChunkBytes);
-    u64* lists = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(sq) + (size_t)dq * 16);
-    u64* bars = lists + (size_t)kBulkWarps * a.k_pad;
+    u64* lists = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(sq) + (size_t)QB * dq * 16);
+    u64* bars = lists + (size_t)QB * kBulkWarps * K;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 ring = smem_u32(ring_all + (size_t)warp * S * kChunkBytes);
@@ -525,50 +536,93 @@ __global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_f32_bulk_kernel(con
         for (u32 i = 0; i < pre; i++) issue();
     }
 
-    for (u32 j = tid; j < dq; j += kBulkThreads) {
-        const u32 c = 4 * j;
+    // stage the queries, zero-padded to a multiple of 4 columns
+    for (u32 t = tid; t < (u32)QB * dq; t += kBulkThreads) {
+        const u32 b = t / dq, j = t - b * dq, c = 4 * j;
+        const float* qp = a.query + (size_t)b * a.dim;
         float4 v;
-        v.x = (c + 0 < a.dim) ? a.query[c + 0] : 0.0f;
-        v.y = (c + 1 < a.dim) ? a.query[c + 1] : 0.0f;
-        v.z = (c + 2 < a.dim) ? a.query[c + 2] : 0.0f;
-        v.w = (c + 3 < a.dim) ? a.query[c + 3] : 0.0f;
-        sq[j] = v;
+        v.x = (c + 0 < a.dim) ? qp[c + 0] : 0.0f;
+        v.y = (c + 1 < a.dim) ? qp[c + 1] : 0.0f;
+        v.z = (c + 2 < a.dim) ? qp[c + 2] : 0.0f;
+        v.w = (c + 3 < a.dim) ? qp[c + 3] : 0.0f;
+        sq[t] = v;
     }
-    WarpTopK top;
-    top.init(lists + (size_t)warp * a.k_pad, a.k, a.k_pad, lane);
+    WarpTopK top[QB];
+#pragma unroll
+    for (int b = 0; b < QB; b++) top[b].init(lists + ((size_t)b * kBulkWarps + warp) * K, a.k, K, lane);
     __syncthreads();
-    float mag_b = 0.0f, qsq = 0.0f;  // |b|: accumulated by every thread during its first panel
+
+    // |b| per query: accumulated by every thread during its first panel (src/metrics.rs:155)
+    float mag_b[QB], qsq[QB], acc[QB];
     bool need_qnorm = true;
+#pragma unroll
+    for (int b = 0; b < QB; b++) mag_b[b] = qsq[b] = acc[b] = 0.0f;
 
     u32 stage = 0, parity = 0, ci = 0, panel = panel0;
-    float acc = 0.0f, mag_a = 0.0f;
-    bool maybe_identical = false;
+    float mag_a = 0.0f;
+    unsigned maybe_mask = 0;  // bit b: columns 0..3 of my row match query b
     for (u32 c = 0; c < n_chunks; c++) {
         const u32 j0 = ci * CH;
         if (ci == 0) {
             const u32 row = panel * kPanelRows + lane;
             mag_a = (row < a.n_rows) ? __ldg(a.norms + row) : 0.0f;
-            acc = 0.0f;
+#pragma unroll
+            for (int b = 0; b < QB; b++) acc[b] = 0.0f;
         }
         mbar_wait(bar0 + stage * 8, parity);
         const float4* sp = ring_v + (size_t)stage * (kChunkBytes / 16) + lane;
-        if (j0 + CH <= dq) {
+        if (QB <= 2 && j0 + CH <= dq) {
+            // narrow batches: pull the whole chunk into registers, then run the chains
             float4 v[CH];
 #pragma unroll
             for (int u = 0; u < CH; u++) v[u] = sp[u * 32];
-            if (ci == 0) maybe_identical = !differs4(v[0], sq[0]);
+            if (ci == 0) {
+                maybe_mask = 0;
 #pragma unroll
-            for (int u = 0; u < CH; u++) acc = dot4_seq(acc, v[u], sq[j0 + u]);
+                for (int b = 0; b < QB; b++) maybe_mask |= differs4(v[0], sq[b * dq]) ? 0u : (1u << b);
+            }
+#pragma unroll
+            for (int u = 0; u < CH; u++) {
+#pragma unroll
+                for (int b = 0; b < QB; b++) acc[b] = dot4_seq(acc[b], v[u], sq[b * dq + j0 + u]);
+            }
             if (need_qnorm) {
 #pragma unroll
-                for (int u = 0; u < CH; u++) qsq = sq4_seq(qsq, sq[j0 + u]);
+                for (int u = 0; u < CH; u++) {
+#pragma unroll
+                    for (int b = 0; b < QB; b++) qsq[b] = sq4_seq(qsq[b], sq[b * dq + j0 + u]);
+                }
+            }
+        } else if (j0 + CH <= dq) {
+            // wide batches: QB independent chains already give the ILP; keep register use flat
+            if (ci == 0) {
+                const float4 v0 = sp[0];
+                maybe_mask = 0;
+#pragma unroll
+                for (int b = 0; b < QB; b++) maybe_mask |= differs4(v0, sq[b * dq]) ? 0u : (1u << b);
+            }
+#pragma unroll 2
+            for (int u = 0; u < CH; u++) {
+                const float4 v = sp[u * 32];
+#pragma unroll
+                for (int b = 0; b < QB; b++) {
+                    const float4 q = sq[b * dq + j0 + u];
+                    acc[b] = dot4_seq(acc[b], v, q);
+                    if (need_qnorm) qsq[b] = sq4_seq(qsq[b], q);
+                }
             }
         } else {
             for (u32 u = 0; j0 + u < dq; u++) {
                 const float4 v = sp[u * 32];
-                if (ci == 0 && u == 0) maybe_identical = !differs4(v, sq[0]);
-                acc = dot4_seq(acc, v, sq[j0 + u]);
-                if (need_qnorm) qsq = sq4_seq(qsq, sq[j0 + u]);
+#pragma unroll
+                for (int b = 0; b < QB; b++) {
+                    if (ci == 0 && u == 0) {
+                        if (b == 0) maybe_mask = 0;
+                        maybe_mask |= differs4(v, sq[b * dq]) ? 0u : (1u << b);
+                    }
+                    acc[b] = dot4_seq(acc[b], v, sq[b * dq + j0 + u]);
+                    if (need_qnorm) qsq[b] = sq4_seq(qsq[b], sq[b * dq + j0 + u]);
+                }
             }
         }
         __syncwarp();  // every lane has consumed this stage: hand it back to the copy engine
@@ -576,17 +630,22 @@ __global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_f32_bulk_kernel(con
 
         if (++ci == cpp) {
             if (need_qnorm) {
-                mag_b = __fsqrt_rn(qsq);
+#pragma unroll
+                for (int b = 0; b < QB; b++) mag_b[b] = __fsqrt_rn(qsq[b]);
                 need_qnorm = false;
             }
             const u32 row = panel * kPanelRows + lane;
-            const bool identical = warp_confirm_identical(
-                maybe_identical && row < a.n_rows, a.panels + (size_t)panel * panel_stride, sq, dq,
-                lane);
-            u64 key = kKeyMax;
-            if (row < a.n_rows)
-                key = make_key(finish_distance(acc, mag_a, mag_b, identical), a.row_base + row);
-            top.offer(key, lane);
+            const bool valid = row < a.n_rows;
+#pragma unroll
+            for (int b = 0; b < QB; b++) {
+                const bool identical = warp_confirm_identical(
+                    valid && ((maybe_mask >> b) & 1u), a.panels + (size_t)panel * panel_stride,
+                    sq + (size_t)b * dq, dq, lane);
+                u64 key = kKeyMax;
+                if (valid)
+                    key = make_key(finish_distance(acc[b], mag_a, mag_b[b], identical), a.row_base + row);
+                top[b].offer(key, lane);
+            }
             ci = 0;
             panel += total_warps;
         }
@@ -595,9 +654,10 @@ __global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_f32_bulk_kernel(con
             parity ^= 1;
         }
     }
-    top.finish(lane);
+#pragma unroll
+    for (int b = 0; b < QB; b++) top[b].finish(lane);
     __syncthreads();
-    scan_epilogue<kBulkWarps>(lists, a.k_pad, a.k, a.cta_keys, a.fin, a.fuse_final != 0);
+    scan_epilogue<kBulkWarps, QB>(lists, K, a.k, a.cta_keys, a.fin, a.fuse_final != 0);
 }
 
 // ------------------------------------------------------------------------------------------
