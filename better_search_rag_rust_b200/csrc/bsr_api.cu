@@ -58,7 +58,8 @@ struct DevBuf {
 
 struct bsr_store {
     int device = 0;
-    u32 dim = 0, dq = 0;
+    u32 dim = 0, dq = 0;  // dq: query quads (f32: ceil(dim/4); bf16: 16 * kb)
+    u32 kb = 0;          // bf16 only: 64-column blocks per row
     bsr_dtype dtype = BSR_F32;
     u64 row_base = 0;
     u64 n_rows = 0;
@@ -125,30 +126,37 @@ static u32 next_pow2(u32 v) {
     return p;
 }
 
-static size_t panel_bytes(const bsr_store* s) { return (size_t)s->dq * 32 * sizeof(float4); }
+static bool is_bf16(const bsr_store* s) { return s->dtype == BSR_BF16; }
+// allocation unit: one 32-row panel (f32) or one 64-row tile (bf16)
+static u32 unit_rows(const bsr_store* s) { return is_bf16(s) ? 64u : 32u; }
+static size_t panel_bytes(const bsr_store* s) {
+    return is_bf16(s) ? (size_t)s->kb * kTileBytes : (size_t)s->dq * 32 * sizeof(float4);
+}
+static size_t used_units(const bsr_store* s, u64 rows) { return (size_t)((rows + unit_rows(s) - 1) / unit_rows(s)); }
 
 // grow the panel/norm allocation to hold at least `rows` rows, preserving contents
 static int reserve_rows(bsr_store* s, u64 rows) {
     if (rows <= s->cap_rows) return BSR_OK;
     u64 want = std::max(rows, s->cap_rows + s->cap_rows / 2);
-    want = (want + 31) & ~31ull;
+    const u64 ur = unit_rows(s);
+    want = (want + ur - 1) / ur * ur;
     const size_t pb = panel_bytes(s);
     float4* np = nullptr;
     float* nn = nullptr;
-    CU(cudaMalloc((void**)&np, (size_t)(want / 32) * pb));
+    CU(cudaMalloc((void**)&np, (size_t)(want / ur) * pb));
     cudaError_t e = cudaMalloc((void**)&nn, (size_t)want * sizeof(float));
     if (e != cudaSuccess) {
         cudaFree(np);
         return fail(BSR_ERR_OOM, "cudaMalloc(norms) failed: %s", cudaGetErrorString(e));
     }
-    const size_t used_panels = (size_t)((s->n_rows + 31) / 32);
+    const size_t used_panels = used_units(s, s->n_rows);
     if (used_panels) {
         CU(cudaMemcpyAsync(np, s->panels, used_panels * pb, cudaMemcpyDeviceToDevice, s->stream));
         CU(cudaMemcpyAsync(nn, s->norms, (size_t)s->n_rows * sizeof(float),
                            cudaMemcpyDeviceToDevice, s->stream));
     }
     // rows past n_rows inside a used panel are already zero; zero everything newly allocated
-    CU(cudaMemsetAsync((char*)np + used_panels * pb, 0, (size_t)(want / 32 - used_panels) * pb,
+    CU(cudaMemsetAsync((char*)np + used_panels * pb, 0, (size_t)(want / ur - used_panels) * pb,
                        s->stream));
     CU(cudaStreamSynchronize(s->stream));
     if (s->panels) CU(cudaFree(s->panels));
@@ -181,7 +189,6 @@ extern "C" int bsr_store_create(int device, uint32_t dim, bsr_dtype dtype, uint6
     *out = nullptr;
     CHECK(dim > 0, BSR_ERR_INVALID, "bsr_store_create: dim must be > 0");
     CHECK(dtype == BSR_F32 || dtype == BSR_BF16, BSR_ERR_INVALID, "bsr_store_create: bad dtype");
-    CHECK(dtype == BSR_F32, BSR_ERR_UNSUPPORTED, "bsr_store_create: BSR_BF16 stores are not built yet");
     CHECK(row_base < 0xFFFFFFFFull, BSR_ERR_INVALID, "bsr_store_create: row_base must fit 32 bits");
     int n_dev = 0;
     CU(cudaGetDeviceCount(&n_dev));
@@ -192,8 +199,9 @@ extern "C" int bsr_store_create(int device, uint32_t dim, bsr_dtype dtype, uint6
     CHECK(s, BSR_ERR_OOM, "bsr_store_create: host allocation failed");
     s->device = device;
     s->dim = dim;
-    s->dq = (dim + 3) / 4;
     s->dtype = dtype;
+    s->kb = (dim + 63) / 64;
+    s->dq = dtype == BSR_BF16 ? s->kb * 16 : (dim + 3) / 4;
     s->row_base = row_base;
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
@@ -240,8 +248,7 @@ extern "C" int bsr_store_reset(bsr_store* s) {
     CHECK(s, BSR_ERR_INVALID, "bsr_store_reset: null store");
     DeviceGuard g(s->device);
     if (s->n_rows) {
-        const size_t used_panels = (size_t)((s->n_rows + 31) / 32);
-        CU(cudaMemsetAsync(s->panels, 0, used_panels * panel_bytes(s), s->stream));
+        CU(cudaMemsetAsync(s->panels, 0, used_units(s, s->n_rows) * panel_bytes(s), s->stream));
         CU(cudaStreamSynchronize(s->stream));
     }
     s->n_rows = 0;
@@ -258,7 +265,11 @@ static int check_room(bsr_store* s, u64 n_rows) {
 static int finish_append(bsr_store* s, u64 n_rows) {
     const u32 lo = (u32)s->n_rows, hi = (u32)(s->n_rows + n_rows);
     const u32 span = hi - (lo & ~31u);
-    row_norms_kernel<<<(span + 255) / 256, 256, 0, s->stream>>>(s->panels, s->norms, lo, hi, s->dq);
+    if (is_bf16(s))
+        row_norms_bf16_kernel<<<(hi - lo + 127) / 128, 128, 0, s->stream>>>(
+            (const unsigned char*)s->panels, s->norms, lo, hi, s->kb);
+    else
+        row_norms_kernel<<<(span + 255) / 256, 256, 0, s->stream>>>(s->panels, s->norms, lo, hi, s->dq);
     s->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s->stream));
@@ -267,6 +278,15 @@ static int finish_append(bsr_store* s, u64 n_rows) {
 }
 
 static int interleave_from_device(bsr_store* s, const float* d_rows, u64 row_lo, u64 n) {
+    if (is_bf16(s)) {
+        const u32 first_tile = (u32)(row_lo >> 6), last_tile = (u32)((row_lo + n - 1) >> 6);
+        const size_t total = (size_t)(last_tile - first_tile + 1) * s->kb * 512;
+        interleave_rows_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(
+            d_rows, (uint4*)s->panels, (u32)row_lo, (u32)n, s->dim, s->kb);
+        s->launches++;
+        CU(cudaGetLastError());
+        return BSR_OK;
+    }
     const u32 first_panel = (u32)(row_lo >> 5);
     const u32 last_panel = (u32)((row_lo + n - 1) >> 5);
     const size_t total = (size_t)(last_panel - first_panel + 1) * s->dq * 128;
@@ -325,6 +345,15 @@ extern "C" int bsr_store_append_synthetic(bsr_store* s, uint64_t seed, uint64_t 
     for (u64 done = 0; done < n_rows; done += chunk) {
         const u64 n = std::min(chunk, n_rows - done);
         const u64 lo = s->n_rows + done;
+        if (is_bf16(s)) {
+            const u32 first_tile = (u32)(lo >> 6), last_tile = (u32)((lo + n - 1) >> 6);
+            const size_t total = (size_t)(last_tile - first_tile + 1) * s->kb * 512;
+            synth_rows_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(
+                (uint4*)s->panels, (u32)lo, (u32)n, s->dim, s->kb, seed, first_row + done);
+            s->launches++;
+            CU(cudaGetLastError());
+            continue;
+        }
         const u32 first_panel = (u32)(lo >> 5), last_panel = (u32)((lo + n - 1) >> 5);
         const size_t total = (size_t)(last_panel - first_panel + 1) * s->dq * 32;
         synth_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(
@@ -357,7 +386,7 @@ extern "C" int bsr_store_device(const bsr_store* s, int* device) {
 }
 extern "C" int bsr_store_scan_bytes(const bsr_store* s, uint64_t* bytes) {
     CHECK(s && bytes, BSR_ERR_INVALID, "bsr_store_scan_bytes: null argument");
-    *bytes = s->n_rows * (u64)s->dq * sizeof(float4);
+    *bytes = is_bf16(s) ? s->n_rows * (u64)s->kb * 128 : s->n_rows * (u64)s->dq * sizeof(float4);
     return BSR_OK;
 }
 
@@ -378,9 +407,14 @@ extern "C" int bsr_store_get_many(const bsr_store* cs, uint64_t offset, uint64_t
     for (u64 done = 0; done < length; done += chunk_rows) {
         const u64 n = std::min(chunk_rows, length - done);
         const size_t total = (size_t)n * s->dim;
-        gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(
-            (const float*)s->panels, (float*)s->staging.p, (u32)(offset + done), (u32)n, s->dim,
-            s->dq);
+        if (is_bf16(s))
+            gather_rows_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(
+                (const unsigned char*)s->panels, (float*)s->staging.p, (u32)(offset + done), (u32)n,
+                s->dim, s->kb);
+        else
+            gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(
+                (const float*)s->panels, (float*)s->staging.p, (u32)(offset + done), (u32)n, s->dim,
+                s->dq);
         s->launches++;
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(out_rows + done * s->dim, s->staging.p, total * sizeof(float),
@@ -480,25 +514,32 @@ static u32 bulk_max_qb(const bsr_store* s, u32 K) {
     return 1;
 }
 
-template <int QB>
-static int launch_scan_bulk(bsr_store* s, const ScanArgs& a, unsigned grid, u32 stages,
-                            cudaStream_t st) {
+template <int QB, bool BF16>
+static int launch_scan_bulk_t(bsr_store* s, const ScanArgs& a, unsigned grid, u32 stages,
+                              cudaStream_t st) {
     static thread_local bool configured[64] = {false};
     if (!configured[s->device & 63]) {
         cudaFuncAttributes fa;
-        CU(cudaFuncGetAttributes(&fa, scan_topk_f32_bulk_kernel<QB>));
-        CU(cudaFuncSetAttribute(scan_topk_f32_bulk_kernel<QB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CU(cudaFuncGetAttributes(&fa, scan_topk_bulk_kernel<QB, BF16>));
+        CU(cudaFuncSetAttribute(scan_topk_bulk_kernel<QB, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(s->smem_optin - fa.sharedSizeBytes)));
         configured[s->device & 63] = true;
     }
     BulkScanArgs ba;
     ba.s = a;
     ba.stages = stages;
-    scan_topk_f32_bulk_kernel<QB>
+    scan_topk_bulk_kernel<QB, BF16>
         <<<grid, kBulkThreads, bulk_smem_bytes(s, a.k_pad, stages, QB), st>>>(ba);
     s->launches++;
     CU(cudaGetLastError());
     return BSR_OK;
+}
+
+template <int QB>
+static int launch_scan_bulk(bsr_store* s, const ScanArgs& a, unsigned grid, u32 stages,
+                            cudaStream_t st) {
+    return is_bf16(s) ? launch_scan_bulk_t<QB, true>(s, a, grid, stages, st)
+                      : launch_scan_bulk_t<QB, false>(s, a, grid, stages, st);
 }
 
 // reduce n_lists lists per query to one; returns the buffer holding [nq][K] in *result
@@ -543,7 +584,8 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
                               u64* d_idx, float* d_dist, u32* d_count, cudaStream_t st) {
     const u32 K = bsr_candidate_slots(k);
     const u32 n_panels = (u32)((s->n_rows + 31) / 32);
-    const bool bulk = scan_variant() == 1 && bulk_stages(s, K, 1) >= 2;
+    const bool bulk = (scan_variant() == 1 || is_bf16(s)) && bulk_stages(s, K, 1) >= 2;
+    CHECK(bulk || !is_bf16(s), BSR_ERR_UNSUPPORTED, "search: BF16 stores need the bulk-async scan kernel");
     const unsigned grid = scan_grid(s, n_panels, bulk ? kBulkWarps : kScanWarps);
     const size_t smem = (size_t)s->dq * sizeof(float4) + (size_t)kScanWarps * K * sizeof(u64);
     CHECK(bulk || smem + 1024 <= s->smem_optin, BSR_ERR_UNSUPPORTED,

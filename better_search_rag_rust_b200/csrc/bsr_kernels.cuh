@@ -57,6 +57,61 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     return v;
 }
 
+// src/metrics.rs:13 -- `(a[i] - b[i]).abs() > 1e-10`; false for NaN.
+__device__ __forceinline__ bool differs(float a, float b) {
+    return fabsf(__fsub_rn(a, b)) > 1e-10f;
+}
+__device__ __forceinline__ bool differs4(const float4& a, const float4& q) {
+    return differs(a.x, q.x) || differs(a.y, q.y) || differs(a.z, q.z) || differs(a.w, q.w);
+}
+
+// ------------------------------------------------------------------------------------------
+// BF16 stores use a second layout, shared by the exact scan and the tensor-core path: tiles of
+// 64 rows x 64 columns (8 KiB), stored in HBM as the shared-memory image tcgen05.mma expects for
+// a K-major operand with 128-byte swizzle (8-row x 128-byte atoms, 16-byte chunks XOR-ed with the
+// row index inside the atom):
+//
+//   byte offset of element (row r, column c) =
+//       ((r/64) * KB + c/64) * 8192 + ((r%64)/8) * 1024 + (r%8) * 128
+//       + ((((c%64)/8) ^ (r%8)) * 16) + (c%8) * 2                      KB = ceil(dim/64)
+//
+// One cp.async.bulk of 8 KiB brings a ready-to-multiply operand tile; the exact scan copies the
+// 4 KiB half (32 rows) its warp owns and reads it conflict-free with the same XOR.
+// ------------------------------------------------------------------------------------------
+constexpr u32 kTileRows = 64;
+constexpr u32 kTileBytes = 8192;
+
+__host__ __device__ __forceinline__ size_t bf16_chunk_offset(u32 row, u32 kb, u32 chunk, u32 KB) {
+    return ((size_t)(row >> 6) * KB + kb) * kTileBytes + ((row & 63u) >> 3) * 1024u + (row & 7u) * 128u +
+           ((chunk ^ (row & 7u)) << 4);
+}
+__device__ __forceinline__ unsigned short f32_to_bf16_rne(float f) {
+    u32 b = __float_as_uint(f);
+    if ((b & 0x7F800000u) == 0x7F800000u && (b & 0x007FFFFFu)) return (unsigned short)((b >> 16) | 0x0040u);
+    b += 0x7FFFu + ((b >> 16) & 1u);
+    return (unsigned short)(b >> 16);
+}
+__device__ __forceinline__ float bf16_lo(u32 packed) { return __uint_as_float(packed << 16); }
+__device__ __forceinline__ float bf16_hi(u32 packed) { return __uint_as_float(packed & 0xFFFF0000u); }
+
+// eight consecutive columns held as packed bf16 (uint4) against two query quads, in column order
+__device__ __forceinline__ float dot8_seq_bf16(float acc, const uint4& a, const float4& q0, const float4& q1) {
+    acc = __fadd_rn(acc, __fmul_rn(bf16_lo(a.x), q0.x));
+    acc = __fadd_rn(acc, __fmul_rn(bf16_hi(a.x), q0.y));
+    acc = __fadd_rn(acc, __fmul_rn(bf16_lo(a.y), q0.z));
+    acc = __fadd_rn(acc, __fmul_rn(bf16_hi(a.y), q0.w));
+    acc = __fadd_rn(acc, __fmul_rn(bf16_lo(a.z), q1.x));
+    acc = __fadd_rn(acc, __fmul_rn(bf16_hi(a.z), q1.y));
+    acc = __fadd_rn(acc, __fmul_rn(bf16_lo(a.w), q1.z));
+    acc = __fadd_rn(acc, __fmul_rn(bf16_hi(a.w), q1.w));
+    return acc;
+}
+__device__ __forceinline__ bool differs8_bf16(const uint4& a, const float4& q0, const float4& q1) {
+    return differs(bf16_lo(a.x), q0.x) || differs(bf16_hi(a.x), q0.y) || differs(bf16_lo(a.y), q0.z) ||
+           differs(bf16_hi(a.y), q0.w) || differs(bf16_lo(a.z), q1.x) || differs(bf16_hi(a.z), q1.y) ||
+           differs(bf16_lo(a.w), q1.z) || differs(bf16_hi(a.w), q1.w);
+}
+
 // One reference step `acc = acc + a_i * b_i` for four consecutive columns: separately rounded
 // multiply and add, never contracted to FMA (rustc does not contract; __fmul_rn/__fadd_rn are
 // exempt from nvcc's -fmad).
@@ -75,14 +130,6 @@ __device__ __forceinline__ float sq4_seq(float acc, const float4& q) {
     acc = __fadd_rn(acc, __fmul_rn(q.z, q.z));
     acc = __fadd_rn(acc, __fmul_rn(q.w, q.w));
     return acc;
-}
-
-// src/metrics.rs:13 -- `(a[i] - b[i]).abs() > 1e-10`; false for NaN.
-__device__ __forceinline__ bool differs(float a, float b) {
-    return fabsf(__fsub_rn(a, b)) > 1e-10f;
-}
-__device__ __forceinline__ bool differs4(const float4& a, const float4& q) {
-    return differs(a.x, q.x) || differs(a.y, q.y) || differs(a.z, q.z) || differs(a.w, q.w);
 }
 
 // src/metrics.rs:157-164 given dot, |a|, |b| and the identity flag (:148-151).
@@ -107,6 +154,27 @@ __device__ __forceinline__ bool warp_confirm_identical(bool maybe, const float4*
         m &= m - 1;
         bool diff = false;
         for (u32 j = lane; j < dq; j += 32) diff |= differs4(panel_base[(size_t)j * 32 + src], sq[j]);
+        const bool any_diff = __any_sync(0xFFFFFFFFu, diff);
+        if (lane == src) identical = !any_diff;
+    }
+    return identical;
+}
+
+// same for a BF16 store: `tiles` is the store base, `row` the flagged lane's local row
+__device__ __forceinline__ bool warp_confirm_identical_bf16(bool maybe, const unsigned char* tiles,
+                                                            u32 row_of_lane0, u32 KB, const float4* sq,
+                                                            int lane) {
+    unsigned m = __ballot_sync(0xFFFFFFFFu, maybe);
+    bool identical = false;
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const u32 row = row_of_lane0 + src;
+        bool diff = false;
+        for (u32 g = lane; g < KB * 8; g += 32) {  // g = 16-byte chunk index along the row
+            const uint4 a = *reinterpret_cast<const uint4*>(tiles + bf16_chunk_offset(row, g >> 3, g & 7u, KB));
+            diff |= differs8_bf16(a, sq[2 * g], sq[2 * g + 1]);
+        }
         const bool any_diff = __any_sync(0xFFFFFFFFu, diff);
         if (lane == src) identical = !any_diff;
     }
@@ -489,10 +557,12 @@ struct BulkScanArgs {
 
 // QB queries share one pass over the store: the row chunk is read from shared memory once and
 // feeds QB independent sequential dot products (a.query -> [QB][dim], outputs indexed by query).
-template <int QB>
-__global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_f32_bulk_kernel(const BulkScanArgs ba) {
+// BF16 selects the tiled bf16 layout (a.panels is then the tile base, a.dq = 16 * KB); the
+// arithmetic is the same sequential binary32 fold over the widened bf16 values.
+template <int QB, bool BF16>
+__global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_bulk_kernel(const BulkScanArgs ba) {
     const ScanArgs& a = ba.s;
-    constexpr int CH = kChunkQuads;
+    constexpr int CH = kChunkQuads;                    // fp32: column-quads per 4 KiB chunk
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const u32 dq = a.dq, S = ba.stages, K = a.k_pad;
     // [ring: W*S*4KiB | queries: QB*dq*16 | lists: QB*W*K*8 | mbarriers: W*S*8]
@@ -502,26 +572,35 @@ __global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_f32_bulk_kernel(con
     u64* bars = lists + (size_t)QB * kBulkWarps * K;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 ring = smem_u32(ring_all + (size_t)warp * S * kChunkBytes);
-    const float4* ring_v = reinterpret_cast<const float4*>(ring_all + (size_t)warp * S * kChunkBytes);
+    const unsigned char* ring_b = ring_all + (size_t)warp * S * kChunkBytes;
+    const u32 ring = smem_u32(ring_b);
     const u32 bar0 = smem_u32(bars + (size_t)warp * S);
+    const unsigned char* store_b = reinterpret_cast<const unsigned char*>(a.panels);
 
     const u32 total_warps = gridDim.x * kBulkWarps;
     const u32 panel0 = blockIdx.x * kBulkWarps + warp;
-    const u32 cpp = (dq + CH - 1) / CH;  // chunks per panel
+    const u32 KB = dq >> 4;                                      // bf16: 64-column blocks
+    const u32 cpp = BF16 ? KB : (dq + CH - 1) / CH;              // chunks per 32-row panel
     const u32 my_panels = panel0 < a.n_panels ? (a.n_panels - 1 - panel0) / total_warps + 1 : 0;
     const u32 n_chunks = my_panels * cpp;
-    const size_t panel_stride = (size_t)dq * 32;  // float4 units
+    const size_t panel_stride = (size_t)dq * 32;                 // fp32 layout, float4 units
     const u64 policy = make_evict_first_policy();
 
     // producer state (meaningful in lane 0): next chunk to request
     u32 ic = 0, ipanel = panel0, ici = 0;
     auto issue = [&]() {
-        const u32 nq = min((u32)CH, dq - ici * CH);
         const u32 st = ic % S;
-        const float4* src = a.panels + (size_t)ipanel * panel_stride + (size_t)ici * CH * 32;
-        mbar_expect_tx(bar0 + st * 8, nq * 512);
-        bulk_g2s(ring + st * kChunkBytes, src, nq * 512, bar0 + st * 8, policy);
+        const void* src;
+        u32 bytes;
+        if (BF16) {  // this warp's 32-row half of tile (ipanel/2), column block ici
+            src = store_b + ((size_t)(ipanel >> 1) * KB + ici) * kTileBytes + (ipanel & 1u) * 4096u;
+            bytes = 4096;
+        } else {
+            src = a.panels + (size_t)ipanel * panel_stride + (size_t)ici * CH * 32;
+            bytes = min((u32)CH, dq - ici * CH) * 512;
+        }
+        mbar_expect_tx(bar0 + st * 8, bytes);
+        bulk_g2s(ring + st * kChunkBytes, src, bytes, bar0 + st * 8, policy);
         ic++;
         if (++ici == cpp) {
             ici = 0;
@@ -536,7 +615,7 @@ __global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_f32_bulk_kernel(con
         for (u32 i = 0; i < pre; i++) issue();
     }
 
-    // stage the queries, zero-padded to a multiple of 4 columns
+    // stage the queries, zero-padded to the padded column count
     for (u32 t = tid; t < (u32)QB * dq; t += kBulkThreads) {
         const u32 b = t / dq, j = t - b * dq, c = 4 * j;
         const float* qp = a.query + (size_t)b * a.dim;
@@ -560,9 +639,8 @@ __global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_f32_bulk_kernel(con
 
     u32 stage = 0, parity = 0, ci = 0, panel = panel0;
     float mag_a = 0.0f;
-    unsigned maybe_mask = 0;  // bit b: columns 0..3 of my row match query b
+    unsigned maybe_mask = 0;  // bit b: the first columns of my row match query b
     for (u32 c = 0; c < n_chunks; c++) {
-        const u32 j0 = ci * CH;
         if (ci == 0) {
             const u32 row = panel * kPanelRows + lane;
             mag_a = (row < a.n_rows) ? __ldg(a.norms + row) : 0.0f;
@@ -570,58 +648,83 @@ __global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_f32_bulk_kernel(con
             for (int b = 0; b < QB; b++) acc[b] = 0.0f;
         }
         mbar_wait(bar0 + stage * 8, parity);
-        const float4* sp = ring_v + (size_t)stage * (kChunkBytes / 16) + lane;
-        if (QB <= 2 && j0 + CH <= dq) {
-            // narrow batches: pull the whole chunk into registers, then run the chains
-            float4 v[CH];
-#pragma unroll
-            for (int u = 0; u < CH; u++) v[u] = sp[u * 32];
+        if (BF16) {
+            // my row inside the 4 KiB half tile: atom lane/8, row lane%8; chunk c at (c ^ row%8)
+            const unsigned char* rp = ring_b + (size_t)stage * kChunkBytes + (lane >> 3) * 1024 + (lane & 7) * 128;
+            const u32 sw = lane & 7;
+            const u32 q0i = ci * 16;  // first query quad of this column block
             if (ci == 0) {
+                const uint4 v0 = *reinterpret_cast<const uint4*>(rp + (sw << 4));
                 maybe_mask = 0;
 #pragma unroll
-                for (int b = 0; b < QB; b++) maybe_mask |= differs4(v[0], sq[b * dq]) ? 0u : (1u << b);
+                for (int b = 0; b < QB; b++)
+                    maybe_mask |= differs8_bf16(v0, sq[b * dq], sq[b * dq + 1]) ? 0u : (1u << b);
             }
-#pragma unroll
-            for (int u = 0; u < CH; u++) {
-#pragma unroll
-                for (int b = 0; b < QB; b++) acc[b] = dot4_seq(acc[b], v[u], sq[b * dq + j0 + u]);
-            }
-            if (need_qnorm) {
-#pragma unroll
-                for (int u = 0; u < CH; u++) {
-#pragma unroll
-                    for (int b = 0; b < QB; b++) qsq[b] = sq4_seq(qsq[b], sq[b * dq + j0 + u]);
-                }
-            }
-        } else if (j0 + CH <= dq) {
-            // wide batches: QB independent chains already give the ILP; keep register use flat
-            if (ci == 0) {
-                const float4 v0 = sp[0];
-                maybe_mask = 0;
-#pragma unroll
-                for (int b = 0; b < QB; b++) maybe_mask |= differs4(v0, sq[b * dq]) ? 0u : (1u << b);
-            }
-#pragma unroll 2
-            for (int u = 0; u < CH; u++) {
-                const float4 v = sp[u * 32];
+#pragma unroll 4
+            for (u32 cc = 0; cc < 8; cc++) {
+                const uint4 v = *reinterpret_cast<const uint4*>(rp + ((cc ^ sw) << 4));
 #pragma unroll
                 for (int b = 0; b < QB; b++) {
-                    const float4 q = sq[b * dq + j0 + u];
-                    acc[b] = dot4_seq(acc[b], v, q);
-                    if (need_qnorm) qsq[b] = sq4_seq(qsq[b], q);
+                    const float4 qa = sq[b * dq + q0i + 2 * cc], qb2 = sq[b * dq + q0i + 2 * cc + 1];
+                    acc[b] = dot8_seq_bf16(acc[b], v, qa, qb2);
+                    if (need_qnorm) qsq[b] = sq4_seq(sq4_seq(qsq[b], qa), qb2);
                 }
             }
         } else {
-            for (u32 u = 0; j0 + u < dq; u++) {
-                const float4 v = sp[u * 32];
+            const u32 j0 = ci * CH;
+            const float4* sp = reinterpret_cast<const float4*>(ring_b + (size_t)stage * kChunkBytes) + lane;
+            if (QB <= 2 && j0 + CH <= dq) {
+                // narrow batches: pull the whole chunk into registers, then run the chains
+                float4 v[CH];
 #pragma unroll
-                for (int b = 0; b < QB; b++) {
-                    if (ci == 0 && u == 0) {
-                        if (b == 0) maybe_mask = 0;
-                        maybe_mask |= differs4(v, sq[b * dq]) ? 0u : (1u << b);
+                for (int u = 0; u < CH; u++) v[u] = sp[u * 32];
+                if (ci == 0) {
+                    maybe_mask = 0;
+#pragma unroll
+                    for (int b = 0; b < QB; b++) maybe_mask |= differs4(v[0], sq[b * dq]) ? 0u : (1u << b);
+                }
+#pragma unroll
+                for (int u = 0; u < CH; u++) {
+#pragma unroll
+                    for (int b = 0; b < QB; b++) acc[b] = dot4_seq(acc[b], v[u], sq[b * dq + j0 + u]);
+                }
+                if (need_qnorm) {
+#pragma unroll
+                    for (int u = 0; u < CH; u++) {
+#pragma unroll
+                        for (int b = 0; b < QB; b++) qsq[b] = sq4_seq(qsq[b], sq[b * dq + j0 + u]);
                     }
-                    acc[b] = dot4_seq(acc[b], v, sq[b * dq + j0 + u]);
-                    if (need_qnorm) qsq[b] = sq4_seq(qsq[b], sq[b * dq + j0 + u]);
+                }
+            } else if (j0 + CH <= dq) {
+                // wide batches: QB independent chains already give the ILP; keep register use flat
+                if (ci == 0) {
+                    const float4 v0 = sp[0];
+                    maybe_mask = 0;
+#pragma unroll
+                    for (int b = 0; b < QB; b++) maybe_mask |= differs4(v0, sq[b * dq]) ? 0u : (1u << b);
+                }
+#pragma unroll 2
+                for (int u = 0; u < CH; u++) {
+                    const float4 v = sp[u * 32];
+#pragma unroll
+                    for (int b = 0; b < QB; b++) {
+                        const float4 q = sq[b * dq + j0 + u];
+                        acc[b] = dot4_seq(acc[b], v, q);
+                        if (need_qnorm) qsq[b] = sq4_seq(qsq[b], q);
+                    }
+                }
+            } else {
+                for (u32 u = 0; j0 + u < dq; u++) {
+                    const float4 v = sp[u * 32];
+#pragma unroll
+                    for (int b = 0; b < QB; b++) {
+                        if (ci == 0 && u == 0) {
+                            if (b == 0) maybe_mask = 0;
+                            maybe_mask |= differs4(v, sq[b * dq]) ? 0u : (1u << b);
+                        }
+                        acc[b] = dot4_seq(acc[b], v, sq[b * dq + j0 + u]);
+                        if (need_qnorm) qsq[b] = sq4_seq(qsq[b], sq[b * dq + j0 + u]);
+                    }
                 }
             }
         }
@@ -638,9 +741,12 @@ __global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_f32_bulk_kernel(con
             const bool valid = row < a.n_rows;
 #pragma unroll
             for (int b = 0; b < QB; b++) {
-                const bool identical = warp_confirm_identical(
-                    valid && ((maybe_mask >> b) & 1u), a.panels + (size_t)panel * panel_stride,
-                    sq + (size_t)b * dq, dq, lane);
+                const bool maybe = valid && ((maybe_mask >> b) & 1u);
+                const bool identical =
+                    BF16 ? warp_confirm_identical_bf16(maybe, store_b, panel * kPanelRows, KB,
+                                                       sq + (size_t)b * dq, lane)
+                         : warp_confirm_identical(maybe, a.panels + (size_t)panel * panel_stride,
+                                                  sq + (size_t)b * dq, dq, lane);
                 u64 key = kKeyMax;
                 if (valid)
                     key = make_key(finish_distance(acc[b], mag_a, mag_b[b], identical), a.row_base + row);
@@ -782,6 +888,66 @@ __global__ void gather_rows_kernel(const float* __restrict__ panels, float* __re
     out[t] = panels[(size_t)(r >> 5) * per_panel + ((size_t)(c >> 2) * 32 + (r & 31)) * 4 + (c & 3)];
 }
 
+// ---- BF16 store (tile layout above) ------------------------------------------------------------
+// thread t owns destination 16-byte chunk t of the tile range starting at tile row_lo/64
+__device__ __forceinline__ void bf16_chunk_coords(size_t t, u32 first_tile, u32 KB, u32& row, u32& col) {
+    const u32 per_tile = KB * 512;  // chunks per 64-row tile
+    const u32 tile = first_tile + (u32)(t / per_tile);
+    const u32 rem = (u32)(t % per_tile);
+    const u32 kb = rem >> 9, in = rem & 511u;
+    const u32 atom = in >> 6, i = (in >> 3) & 7u, pos = in & 7u;
+    row = tile * 64 + atom * 8 + i;
+    col = kb * 64 + ((pos ^ i) << 3);
+}
+__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
+    uint4 o;
+    o.x = (u32)f32_to_bf16_rne(v[0]) | ((u32)f32_to_bf16_rne(v[1]) << 16);
+    o.y = (u32)f32_to_bf16_rne(v[2]) | ((u32)f32_to_bf16_rne(v[3]) << 16);
+    o.z = (u32)f32_to_bf16_rne(v[4]) | ((u32)f32_to_bf16_rne(v[5]) << 16);
+    o.w = (u32)f32_to_bf16_rne(v[6]) | ((u32)f32_to_bf16_rne(v[7]) << 16);
+    return o;
+}
+__global__ void interleave_rows_bf16_kernel(const float* __restrict__ src, uint4* __restrict__ tiles,
+                                            u32 row_lo, u32 n, u32 dim, u32 KB) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 row, col;
+    bf16_chunk_coords(t, row_lo >> 6, KB, row, col);
+    if (row < row_lo || row >= row_lo + n) return;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[e] = (col + e < dim) ? src[(size_t)(row - row_lo) * dim + col + e] : 0.0f;
+    tiles[(size_t)(row_lo >> 6) * KB * 512 + t] = pack8_bf16(v);
+}
+__global__ void synth_rows_bf16_kernel(uint4* __restrict__ tiles, u32 row_lo, u32 n, u32 dim, u32 KB,
+                                       u64 seed, u64 gen_first_row);
+__global__ void gather_rows_bf16_kernel(const unsigned char* __restrict__ tiles, float* __restrict__ out,
+                                        u32 offset, u32 length, u32 dim, u32 KB) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)length * dim) return;
+    const u32 r = offset + (u32)(t / dim), c = (u32)(t % dim);
+    const unsigned short h = *reinterpret_cast<const unsigned short*>(
+        tiles + bf16_chunk_offset(r, c >> 6, (c & 63u) >> 3, KB) + (c & 7u) * 2);
+    out[t] = __uint_as_float((u32)h << 16);
+}
+// |a| over the bf16-rounded values, sequential (src/metrics.rs:154 on the rounded row)
+__global__ void row_norms_bf16_kernel(const unsigned char* __restrict__ tiles, float* __restrict__ norms,
+                                      u32 row_lo, u32 row_hi, u32 KB) {
+    const u32 row = row_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= row_hi) return;
+    float s = 0.0f;
+    for (u32 g = 0; g < KB * 8; g++) {
+        const uint4 a = *reinterpret_cast<const uint4*>(tiles + bf16_chunk_offset(row, g >> 3, g & 7u, KB));
+        const u32 w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const float lo = bf16_lo(w[e]), hi = bf16_hi(w[e]);
+            s = __fadd_rn(s, __fmul_rn(lo, lo));
+            s = __fadd_rn(s, __fmul_rn(hi, hi));
+        }
+    }
+    norms[row] = __fsqrt_rn(s);
+}
+
 // counter-based uniform(-1,1) generator, identical to bsr_oracle_generate_rows (oracle/) and
 // mirroring the value distribution of the reference fixture (src/utils.rs:14-23).
 __host__ __device__ __forceinline__ u64 splitmix64(u64 z) {
@@ -812,6 +978,19 @@ __global__ void synth_rows_kernel(float4* __restrict__ panels, u32 row_lo, u32 n
     v.z = (c + 2 < dim) ? synth_elem(rk, c + 2) : 0.0f;
     v.w = (c + 3 < dim) ? synth_elem(rk, c + 3) : 0.0f;
     panels[(size_t)panel * per_panel + d] = v;
+}
+
+__global__ void synth_rows_bf16_kernel(uint4* __restrict__ tiles, u32 row_lo, u32 n, u32 dim, u32 KB,
+                                       u64 seed, u64 gen_first_row) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 row, col;
+    bf16_chunk_coords(t, row_lo >> 6, KB, row, col);
+    if (row < row_lo || row >= row_lo + n) return;
+    const u64 rk = splitmix64(seed ^ ((gen_first_row + (row - row_lo)) * 0x9E3779B97F4A7C15ull));
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[e] = (col + e < dim) ? synth_elem(rk, col + e) : 0.0f;
+    tiles[(size_t)(row_lo >> 6) * KB * 512 + t] = pack8_bf16(v);
 }
 
 }  // namespace bsr
