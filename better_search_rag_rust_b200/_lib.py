@@ -66,6 +66,7 @@ SIGNATURES = {
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "bsr_merge_host": (C.c_int, [_store, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p,
                                  C.c_void_p, _u32p]),
+    "bsr_store_set_tensor_min_batch": (C.c_int, [_store, C.c_uint32]),
     "bsr_store_launch_count": (C.c_int, [_store, _u64p]),
     "bsr_store_last_scan_ms": (C.c_int, [_store, _f32p]),
     "bsr_store_set_profiling": (C.c_int, [_store, C.c_int]),

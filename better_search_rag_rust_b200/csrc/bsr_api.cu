@@ -12,6 +12,7 @@
 
 #include "../../include/bsr.h"
 #include "bsr_kernels.cuh"
+#include "bsr_tensor.cuh"
 
 using namespace bsr;
 
@@ -71,7 +72,8 @@ struct bsr_store {
     size_t smem_optin = 0;
 
     // per-search scratch (grown on demand)
-    DevBuf cta_keys, merge_a, merge_b, d_queries, d_cand, d_result, d_counter, staging;
+    DevBuf cta_keys, merge_a, merge_b, d_queries, d_cand, d_result, d_counter, d_gtau, d_surv, staging;
+    u32 tensor_min_batch = 32;  // BF16 stores: batches at least this large use the tcgen05 path (0 = never)
     void* h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
 
@@ -212,6 +214,7 @@ extern "C" int bsr_store_create(int device, uint32_t dim, bsr_dtype dtype, uint6
         delete s;
         return fail(BSR_ERR_CUDA, "bsr_store_create: %s", cudaGetErrorString(e));
     }
+    if (const char* e = getenv("BSR_TENSOR_MIN_BATCH")) s->tensor_min_batch = (u32)std::max(0, atoi(e));
     s->n_sm = prop.multiProcessorCount;
     s->smem_optin = prop.sharedMemPerBlockOptin;
     if (capacity_rows) {
@@ -230,7 +233,7 @@ extern "C" int bsr_store_destroy(bsr_store* s) {
     DeviceGuard g(s->device);
     cudaStreamSynchronize(s->stream);
     DevBuf* bufs[] = {&s->cta_keys, &s->merge_a, &s->merge_b, &s->d_queries,
-                      &s->d_cand,   &s->d_result, &s->d_counter, &s->staging};
+                      &s->d_cand,   &s->d_result, &s->d_counter, &s->d_gtau, &s->d_surv, &s->staging};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (s->panels) cudaFree(s->panels);
@@ -578,11 +581,87 @@ static unsigned scan_grid(const bsr_store* s, u32 n_panels, int warps_per_cta) {
     return std::max(1u, std::min<unsigned>((unsigned)s->n_sm, need));
 }
 
+// ---- tcgen05 path (BF16 stores, large batches) -------------------------------------------------
+static size_t tensor_smem_bytes(u32 K, u32 stages) {
+    return (size_t)stages * kTileBytes + (size_t)K * kTcQ * sizeof(float) + 4 * kTcN * sizeof(float) +
+           kTcQ * sizeof(u32) + (size_t)(2 * stages + 5) * sizeof(u64) + 16 + 1024;  // + ring alignment slack
+}
+static u32 tensor_stages(const bsr_store* s, u32 K) {
+    // >= 4 stages so the idle ring can hold the end-of-kernel sort scratch (4 warps x 8 KiB)
+    u32 st = 12;
+    if (const char* e = getenv("BSR_TENSOR_STAGES")) st = std::max(4, atoi(e));
+    while (st >= 4 && tensor_smem_bytes(K, st) + 2048 > s->smem_optin) st--;
+    return st;
+}
+static bool tensor_eligible(const bsr_store* s, u32 nq, u32 K) {
+    return is_bf16(s) && s->tensor_min_batch > 0 && nq >= s->tensor_min_batch && s->kb <= kTcMaxKB &&
+           K <= 128 && tensor_stages(s, K) >= 4;
+}
+
+static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u64* d_cand, u64* d_idx,
+                         float* d_dist, u32* d_count, cudaStream_t st) {
+    const u32 K = bsr_candidate_slots(k);
+    const u32 n_tiles = (u32)((s->n_rows + kTcN - 1) / kTcN);
+    const unsigned grid = std::max(1u, std::min<unsigned>((unsigned)s->n_sm, n_tiles));
+    const u32 stages = tensor_stages(s, K);
+    const size_t smem = tensor_smem_bytes(K, stages);
+    static thread_local bool configured[64] = {false};
+    if (!configured[s->device & 63]) {
+        cudaFuncAttributes fa;
+        CU(cudaFuncGetAttributes(&fa, scan_topk_bf16_tensor_kernel));
+        CU(cudaFuncSetAttribute(scan_topk_bf16_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(s->smem_optin - fa.sharedSizeBytes)));
+        configured[s->device & 63] = true;
+    }
+    TRY(ensure(s->cta_keys, (size_t)nq * grid * K * sizeof(u64)));
+    TRY(ensure(s->d_gtau, (size_t)kTcQ * k * sizeof(u32)));
+    TRY(ensure(s->d_surv, (size_t)kTcQ * grid * kTcSurvivorCap * sizeof(u64)));
+    const u32 max_per_cta = std::max<u32>(2, kMergeMaxKeys / K);
+    const size_t inter = (size_t)nq * ((grid + max_per_cta - 1) / max_per_cta) * K * sizeof(u64);
+    TRY(ensure(s->merge_a, inter));
+    TRY(ensure(s->merge_b, inter));
+    CU(cudaEventRecord(s->ev_scan0, st));
+    for (u32 q0 = 0; q0 < nq; q0 += kTcQ) {
+        TensorScanArgs a;
+        a.tiles = (const unsigned char*)s->panels;
+        a.norms = s->norms;
+        a.queries = d_queries + (size_t)q0 * s->dim;
+        a.cta_keys = (u64*)s->cta_keys.p + (size_t)q0 * grid * K;
+        a.g_gm = (u32*)s->d_gtau.p;
+        a.survivors = (u64*)s->d_surv.p;
+        a.nq_valid = std::min(kTcQ, nq - q0);
+        a.n_rows = (u32)s->n_rows;
+        a.n_tiles = n_tiles;
+        a.KB = s->kb;
+        a.dim = s->dim;
+        a.k = k;
+        a.k_pad = K;
+        a.row_base = (u32)s->row_base;
+        a.stages = stages;
+        CU(cudaMemsetAsync(s->d_gtau.p, 0, (size_t)kTcQ * k * sizeof(u32), st));  // ordered(-inf) > 0: empty
+        TRY(prof_begin(s, st));
+        scan_topk_bf16_tensor_kernel<<<grid, kTcThreads, smem, st>>>(a);
+        s->launches++;
+        CU(cudaGetLastError());
+        TRY(prof_end(s, st));
+    }
+    CU(cudaEventRecord(s->ev_scan1, st));
+    s->scan_timed = true;
+    TRY(merge_tree(s, (const u64*)s->cta_keys.p, grid, nq, K, K, (size_t)grid * K, d_cand, st));
+    if (d_idx) {
+        unpack_kernel<<<nq, 128, 0, st>>>(d_cand, K, k, d_idx, d_dist, d_count);
+        s->launches++;
+        CU(cudaGetLastError());
+    }
+    return BSR_OK;
+}
+
 // Scan + merge for nq queries.  Always writes the merged candidates to d_cand[nq][K]; when d_idx
 // is non-null also the unpacked idx[nq][k], dist[nq][k], count[nq].
 static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 k, u64* d_cand,
                               u64* d_idx, float* d_dist, u32* d_count, cudaStream_t st) {
     const u32 K = bsr_candidate_slots(k);
+    if (tensor_eligible(s, nq, K)) return search_tensor(s, d_queries, nq, k, d_cand, d_idx, d_dist, d_count, st);
     const u32 n_panels = (u32)((s->n_rows + 31) / 32);
     const bool bulk = (scan_variant() == 1 || is_bf16(s)) && bulk_stages(s, K, 1) >= 2;
     CHECK(bulk || !is_bf16(s), BSR_ERR_UNSUPPORTED, "search: BF16 stores need the bulk-async scan kernel");
@@ -831,5 +910,11 @@ extern "C" int bsr_store_scan_profile(bsr_store* s, double* total_ms, uint64_t* 
     TRY(prof_fold(s));
     *total_ms = s->prof_ms;
     *n_scans = s->prof_scans;
+    return BSR_OK;
+}
+
+extern "C" int bsr_store_set_tensor_min_batch(bsr_store* s, uint32_t min_batch) {
+    CHECK(s, BSR_ERR_INVALID, "bsr_store_set_tensor_min_batch: null store");
+    s->tensor_min_batch = min_batch;
     return BSR_OK;
 }

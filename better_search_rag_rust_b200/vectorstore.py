@@ -235,6 +235,10 @@ class GpuVectorstore:
         _lib.check(_lib.lib().bsr_store_launch_count(self.handle, C.byref(n)))
         return int(n.value)
 
+    def set_tensor_min_batch(self, min_batch: int) -> None:
+        """BF16 stores: smallest query batch that uses the tcgen05 path (0 = always exact scan)."""
+        _lib.check(_lib.lib().bsr_store_set_tensor_min_batch(self.handle, int(min_batch)))
+
     def set_profiling(self, enabled: bool) -> None:
         _lib.check(_lib.lib().bsr_store_set_profiling(self.handle, 1 if enabled else 0))
 

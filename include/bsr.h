@@ -159,6 +159,13 @@ BSR_API int bsr_unpack_device(bsr_store *store, const uint64_t *d_candidates, ui
 BSR_API int bsr_merge_host(bsr_store *store, const uint64_t *idx, const float *dist, uint64_t n,
                            uint32_t top_k, uint64_t *out_idx, float *out_dist, uint32_t *out_count);
 
+/* BF16 stores only: query batches of at least `min_batch` queries (default 32) are scanned on the
+ * tensor cores (tcgen05, queries in tensor memory).  That path is not bit-exact: the tensor core
+ * accumulates the (exact) bf16 products in a different order, so distances agree with the exact
+ * path to ~1e-6.  0 disables it: every search then uses the exact scan.  Needs dim <= 768 and
+ * top_k <= 128; other shapes always use the exact scan. */
+BSR_API int bsr_store_set_tensor_min_batch(bsr_store *store, uint32_t min_batch);
+
 /* ---- introspection for the benchmark harness ---------------------------------------------- */
 
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
