@@ -67,6 +67,7 @@ struct bsr_store {
     u64 cap_rows = 0;  // multiple of 32
     float4* panels = nullptr;
     float* norms = nullptr;
+    float* inv_norms = nullptr;  // 1/|a| (0 where |a| is 0/inf/NaN): the tensor path's cheap score scale
     cudaStream_t stream = nullptr;
     int n_sm = 0;
     size_t smem_optin = 0;
@@ -146,15 +147,22 @@ static int reserve_rows(bsr_store* s, u64 rows) {
     float4* np = nullptr;
     float* nn = nullptr;
     CU(cudaMalloc((void**)&np, (size_t)(want / ur) * pb));
+    float* ni = nullptr;
     cudaError_t e = cudaMalloc((void**)&nn, (size_t)want * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ni, (size_t)want * sizeof(float));
     if (e != cudaSuccess) {
         cudaFree(np);
+        if (nn) cudaFree(nn);
         return fail(BSR_ERR_OOM, "cudaMalloc(norms) failed: %s", cudaGetErrorString(e));
     }
+    CU(cudaMemsetAsync(nn, 0, (size_t)want * sizeof(float), s->stream));
+    CU(cudaMemsetAsync(ni, 0, (size_t)want * sizeof(float), s->stream));
     const size_t used_panels = used_units(s, s->n_rows);
     if (used_panels) {
         CU(cudaMemcpyAsync(np, s->panels, used_panels * pb, cudaMemcpyDeviceToDevice, s->stream));
         CU(cudaMemcpyAsync(nn, s->norms, (size_t)s->n_rows * sizeof(float),
+                           cudaMemcpyDeviceToDevice, s->stream));
+        CU(cudaMemcpyAsync(ni, s->inv_norms, (size_t)s->n_rows * sizeof(float),
                            cudaMemcpyDeviceToDevice, s->stream));
     }
     // rows past n_rows inside a used panel are already zero; zero everything newly allocated
@@ -163,8 +171,10 @@ static int reserve_rows(bsr_store* s, u64 rows) {
     CU(cudaStreamSynchronize(s->stream));
     if (s->panels) CU(cudaFree(s->panels));
     if (s->norms) CU(cudaFree(s->norms));
+    if (s->inv_norms) CU(cudaFree(s->inv_norms));
     s->panels = np;
     s->norms = nn;
+    s->inv_norms = ni;
     s->cap_rows = want;
     return BSR_OK;
 }
@@ -238,6 +248,7 @@ extern "C" int bsr_store_destroy(bsr_store* s) {
         if (b->p) cudaFree(b->p);
     if (s->panels) cudaFree(s->panels);
     if (s->norms) cudaFree(s->norms);
+    if (s->inv_norms) cudaFree(s->inv_norms);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
     if (s->ev_scan0) cudaEventDestroy(s->ev_scan0);
@@ -270,7 +281,7 @@ static int finish_append(bsr_store* s, u64 n_rows) {
     const u32 span = hi - (lo & ~31u);
     if (is_bf16(s))
         row_norms_bf16_kernel<<<(hi - lo + 127) / 128, 128, 0, s->stream>>>(
-            (const unsigned char*)s->panels, s->norms, lo, hi, s->kb);
+            (const unsigned char*)s->panels, s->norms, s->inv_norms, lo, hi, s->kb);
     else
         row_norms_kernel<<<(span + 255) / 256, 256, 0, s->stream>>>(s->panels, s->norms, lo, hi, s->dq);
     s->launches++;
@@ -582,20 +593,26 @@ static unsigned scan_grid(const bsr_store* s, u32 n_panels, int warps_per_cta) {
 }
 
 // ---- tcgen05 path (BF16 stores, large batches) -------------------------------------------------
+static u32 tensor_stage_kb() {
+    u32 v = kTcStageKB;
+    if (const char* e = getenv("BSR_TENSOR_STAGE_KB")) v = (u32)std::min<int>(kTcStageKB, std::max(1, atoi(e)));
+    return v;
+}
 static size_t tensor_smem_bytes(u32 K, u32 stages) {
-    return (size_t)stages * kTileBytes + (size_t)K * kTcQ * sizeof(float) + 4 * kTcN * sizeof(float) +
-           kTcQ * sizeof(u32) + (size_t)(2 * stages + 5) * sizeof(u64) + 16 + 1024;  // + ring alignment slack
+    (void)K;
+    return (size_t)stages * tensor_stage_kb() * kTileBytes + (size_t)kTcNormSlots * 2 * kTcN * sizeof(float) +
+           (size_t)(2 * stages + 5 + 2 * kTcNormSlots) * sizeof(u64) + 16 + 1024;  // + ring alignment slack
 }
 static u32 tensor_stages(const bsr_store* s, u32 K) {
-    // >= 4 stages so the idle ring can hold the end-of-kernel sort scratch (4 warps x 8 KiB)
-    u32 st = 12;
-    if (const char* e = getenv("BSR_TENSOR_STAGES")) st = std::max(4, atoi(e));
-    while (st >= 4 && tensor_smem_bytes(K, st) + 2048 > s->smem_optin) st--;
+    // 48 KiB stages; even one holds the end-of-kernel sort scratch (4 warps x 8 KiB)
+    u32 st = 3;
+    if (const char* e = getenv("BSR_TENSOR_STAGES")) st = std::max(2, atoi(e));
+    while (st >= 2 && tensor_smem_bytes(K, st) + 2048 > s->smem_optin) st--;
     return st;
 }
 static bool tensor_eligible(const bsr_store* s, u32 nq, u32 K) {
     return is_bf16(s) && s->tensor_min_batch > 0 && nq >= s->tensor_min_batch && s->kb <= kTcMaxKB &&
-           K <= 128 && tensor_stages(s, K) >= 4;
+           K <= 128 && tensor_stages(s, K) >= 2;
 }
 
 static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u64* d_cand, u64* d_idx,
@@ -614,8 +631,10 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
         configured[s->device & 63] = true;
     }
     TRY(ensure(s->cta_keys, (size_t)nq * grid * K * sizeof(u64)));
-    TRY(ensure(s->d_gtau, (size_t)kTcQ * k * sizeof(u32)));
-    TRY(ensure(s->d_surv, (size_t)kTcQ * grid * kTcSurvivorCap * sizeof(u64)));
+    const size_t gm_bytes = (size_t)kTcQ * ((k + kTcN - 1) / kTcN) * kTcN * sizeof(u32);
+    TRY(ensure(s->d_gtau, gm_bytes));
+    TRY(ensure(s->d_surv, (size_t)kTcQ * grid * 2 * kTcSurvivorCap * sizeof(u64) + (size_t)kTcQ * grid * sizeof(u32) +
+                              kTcQ * sizeof(float)));
     const u32 max_per_cta = std::max<u32>(2, kMergeMaxKeys / K);
     const size_t inter = (size_t)nq * ((grid + max_per_cta - 1) / max_per_cta) * K * sizeof(u64);
     TRY(ensure(s->merge_a, inter));
@@ -625,10 +644,13 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
         TensorScanArgs a;
         a.tiles = (const unsigned char*)s->panels;
         a.norms = s->norms;
+        a.inv_norms = s->inv_norms;
         a.queries = d_queries + (size_t)q0 * s->dim;
         a.cta_keys = (u64*)s->cta_keys.p + (size_t)q0 * grid * K;
         a.g_gm = (u32*)s->d_gtau.p;
         a.survivors = (u64*)s->d_surv.p;
+        a.surv_count = (u32*)((char*)s->d_surv.p + (size_t)kTcQ * grid * 2 * kTcSurvivorCap * sizeof(u64));
+        a.q_mag = (float*)(a.surv_count + (size_t)kTcQ * grid);
         a.nq_valid = std::min(kTcQ, nq - q0);
         a.n_rows = (u32)s->n_rows;
         a.n_tiles = n_tiles;
@@ -638,11 +660,18 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
         a.k_pad = K;
         a.row_base = (u32)s->row_base;
         a.stages = stages;
-        CU(cudaMemsetAsync(s->d_gtau.p, 0, (size_t)kTcQ * k * sizeof(u32), st));  // ordered(-inf) > 0: empty
+        a.stage_kb = tensor_stage_kb();
+        CU(cudaMemsetAsync(s->d_gtau.p, 0, gm_bytes, st));  // 0 < ordered(-inf): "nobody published yet"
         TRY(prof_begin(s, st));
         scan_topk_bf16_tensor_kernel<<<grid, kTcThreads, smem, st>>>(a);
         s->launches++;
         CU(cudaGetLastError());
+        {
+            const u32 lists = a.nq_valid * grid, wpb = 4;  // 4 warps x 8 KiB of sort scratch per CTA
+            finalize_survivors_kernel<<<(lists + wpb - 1) / wpb, wpb * 32, wpb * kTcSurvivorCap * sizeof(u64), st>>>(a, grid);
+            s->launches++;
+            CU(cudaGetLastError());
+        }
         TRY(prof_end(s, st));
     }
     CU(cudaEventRecord(s->ev_scan1, st));

@@ -931,7 +931,7 @@ __global__ void gather_rows_bf16_kernel(const unsigned char* __restrict__ tiles,
 }
 // |a| over the bf16-rounded values, sequential (src/metrics.rs:154 on the rounded row)
 __global__ void row_norms_bf16_kernel(const unsigned char* __restrict__ tiles, float* __restrict__ norms,
-                                      u32 row_lo, u32 row_hi, u32 KB) {
+                                      float* __restrict__ inv_norms, u32 row_lo, u32 row_hi, u32 KB) {
     const u32 row = row_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= row_hi) return;
     float s = 0.0f;
@@ -945,7 +945,10 @@ __global__ void row_norms_bf16_kernel(const unsigned char* __restrict__ tiles, f
             s = __fadd_rn(s, __fmul_rn(hi, hi));
         }
     }
-    norms[row] = __fsqrt_rn(s);
+    const float na = __fsqrt_rn(s);
+    norms[row] = na;
+    // scale for the tensor path's bound test only (exact distances always divide by |a|)
+    inv_norms[row] = (na > 0.0f && na < INFINITY) ? __fdiv_rn(1.0f, na) : 0.0f;
 }
 
 // counter-based uniform(-1,1) generator, identical to bsr_oracle_generate_rows (oracle/) and

@@ -15,14 +15,16 @@
 // * epilogue: TMEM lane q belongs to thread q, which reads its query's 64 scores with tcgen05.ld
 //   and selects that query's candidates privately -- no cross-thread reduction.  Selection is
 //   bound-based so the common case is branch-free:
-//     - rows are split into k residue classes (row mod k); per query the best normalised score of
-//       every class is tracked with one LDS + FMNMX + STS per score (gm[class]).  The minimum over
-//       the k classes certifies k DISTINCT rows at least that good, so any row below it (minus a
-//       1e-6 safety margin) cannot be in the top-k.  Class maxima are merged across CTAs through a
+//     - rows are split into kc = 64*T >= k classes (position of the row inside its 64-row tile, times
+//       the CTA's group blockIdx % T); per query the best normalised score of each of the CTA's 64
+//       classes is tracked in REGISTERS with one FMNMX per score.  The minimum over all kc classes
+//       certifies kc >= k DISTINCT rows at least that good, so any row below it (minus a 1e-6
+//       safety margin) cannot be in the top-k.  Class maxima are merged across CTAs through a
 //       global array (atomicMax), so the bound reflects every row the whole grid has seen.
-//     - a score is tested with one multiply + compare; only survivors (a fraction ~k ln(n)/n) get
-//       the reference's distance formula (src/metrics.rs:157-164) and are appended, unsorted, to
-//       the (CTA, query) survivor buffer in global memory.
+//     - a score is tested with one multiply + compare; only survivors (a fraction ~k ln(n)/n) are
+//       appended, as raw (row, score) pairs, to the (CTA, query) survivor buffer in global memory.
+//       The reference's distance formula (src/metrics.rs:157-164) runs once per survivor at the
+//       end of the kernel, a warp per query.
 //     - the first kTcLearnTiles tiles of a CTA only feed the class maxima ("learn") and are scanned
 //       again at the end, when the bound is mature.
 //     - at the end each warp bitonic-sorts its queries' survivors and writes the best k_pad.
@@ -43,19 +45,26 @@ constexpr u32 kTcQ = 128;        // queries per CTA  (UMMA M)
 constexpr u32 kTcN = 64;         // store rows per tile (UMMA N)
 constexpr u32 kTcAccCols = 128;  // two 64-column fp32 accumulators at TMEM columns [0, 128)
 constexpr u32 kTcMaxKB = 12;     // A operand: 32 columns per 64-element block, 384 columns at most
+constexpr u32 kTcStageKB = 12;   // max 64-column blocks per ring stage: one cp.async.bulk each (a single
+                                 // thread issuing 8 KiB copies cannot keep an SM fed: ~300 cycles each)
+constexpr u32 kTcStageBytes = kTcStageKB * kTileBytes;
 constexpr u32 kTcLearnTiles = 8; // tiles scanned bound-only first, then again at the end
 constexpr u32 kTcSurvivorCap = 1024;  // survivor slots per (CTA, query)
-constexpr u32 kTcRefresh = 8;    // tiles between merges of the class maxima with the global array
+constexpr u32 kTcNormSlots = 16; // ring of per-tile (|a|, 1/|a|) blocks brought in by TMA (the producer runs ~5 tiles ahead of the epilogue)
 
 struct TensorScanArgs {
     const unsigned char* tiles;  // BF16 store (tile layout)
     const float* norms;          // |a| per row
+    const float* inv_norms;      // 1/|a| per row (0 where |a| is 0, inf or NaN)
     const float* queries;        // [nq_valid][dim] binary32, device
     u64* cta_keys;               // [nq_valid][gridDim.x][k_pad]
-    u32* g_gm;                   // [128][k] global class maxima (ordered-float bits), 0 before the launch
-    u64* survivors;              // [128][gridDim.x][kTcSurvivorCap]
+    u32* g_gm;                   // [64*T][128] global class maxima (ordered-float bits), 0 before the launch
+    u64* survivors;              // [128][gridDim.x][2 * kTcSurvivorCap] raw (row, score) pairs
+    u32* surv_count;             // [128][gridDim.x] survivors per (query, CTA)
+    float* q_mag;                // [128] |b| of the bf16-rounded queries (written by CTA 0)
     u32 nq_valid;                // <= 128
     u32 n_rows, n_tiles, KB, dim, k, k_pad, row_base, stages;
+    u32 stage_kb;                // 64-column blocks per ring stage (<= kTcStageKB)
 };
 
 // ---- tcgen05 wrappers -----------------------------------------------------------------------------
@@ -130,18 +139,19 @@ __device__ __noinline__ bool row_equals_query_bf16(const unsigned char* tiles, u
     return true;
 }
 
-// Rare path, deliberately out of line (the unrolled score loop must stay small enough for the
-// instruction cache): exact distance of one surviving (row, query) pair, appended to the survivor
-// buffer.  An overflowing buffer (adversarial row order only) is compacted to its best k, exactly.
-struct SurvivorState {
-    u64* buf;       // survivor slots of this (CTA, query)
-    u32 cnt;
-    u64 tau_exact;  // k-th best after a compaction, else UINT64_MAX
-};
-__device__ __noinline__ void tc_survivor(SurvivorState& st, const TensorScanArgs& a, const float* qp, u32 row,
-                                         float score, float na, float mag_b, bool tiny_q) {
+// A survivor is stored raw: (local row << 32) | score bits.  Its exact distance -- the reference
+// formula, src/metrics.rs:148-164 -- is computed once, at the end of the kernel.
+__device__ __forceinline__ u64 pack_survivor(u32 row, float score) {
+    return ((u64)row << 32) | (u64)__float_as_uint(score);
+}
+__device__ __forceinline__ u64 survivor_key(const TensorScanArgs& a, u64 raw, const float* qp, float mag_b) {
+    const u32 row = (u32)(raw >> 32);
+    const float score = __uint_as_float((u32)raw);
+    const float na = __ldg(a.norms + row);
     float dist = 1.0f;  // zero magnitude (src/metrics.rs:157-159)
-    bool maybe_identical = tiny_q;
+    // identity (src/metrics.rs:148-151) precedes every other rule; within 1e-10 per element implies
+    // sim ~ 1 unless the query is tiny (|b| < 1e-6), in which case every survivor is checked
+    bool maybe_identical = !(mag_b >= 1e-6f);
     if (na != 0.0f && mag_b != 0.0f) {
         float sim = __fdiv_rn(score, __fmul_rn(na, mag_b));
         sim = fminf(fmaxf(sim, -1.0f), 1.0f);
@@ -149,41 +159,44 @@ __device__ __noinline__ void tc_survivor(SurvivorState& st, const TensorScanArgs
         maybe_identical |= sim >= 0.99999f;
     }
     if (maybe_identical && row_equals_query_bf16(a.tiles, row, a.KB, a.dim, qp)) dist = 0.0f;
-    const u64 key = make_key(dist, a.row_base + row);
-    if (!(key < st.tau_exact)) return;
-    st.buf[st.cnt++] = key;
-    if (st.cnt == kTcSurvivorCap) {
-        const u32 k = a.k;
-        for (u32 x = 0; x < k; x++) {
-            u32 best = x;
-            for (u32 y = x + 1; y < st.cnt; y++)
-                if (st.buf[y] < st.buf[best]) best = y;
-            const u64 tmp = st.buf[x];
-            st.buf[x] = st.buf[best];
-            st.buf[best] = tmp;
-        }
-        st.cnt = k;
-        st.tau_exact = st.buf[k - 1];
+    return make_key(dist, a.row_base + row);
+}
+// Overflowing survivor buffer (adversarial row order only): keep, exactly, the k best of the cap
+// entries.  Out of line: it must not bloat the score loop.  Returns the exact k-th best key.
+__device__ __noinline__ u64 compact_survivors(const TensorScanArgs& a, u64* buf, u32 n, const float* qp,
+                                              float mag_b, u64* keys_tmp) {
+    const u32 k = a.k;
+    for (u32 i = 0; i < n; i++) keys_tmp[i] = survivor_key(a, buf[i], qp, mag_b);
+    for (u32 x = 0; x < k; x++) {  // selection of the k smallest keys, entries move with their keys
+        u32 best = x;
+        for (u32 y = x + 1; y < n; y++)
+            if (keys_tmp[y] < keys_tmp[best]) best = y;
+        const u64 tk = keys_tmp[x], tb = buf[x];
+        keys_tmp[x] = keys_tmp[best];
+        buf[x] = buf[best];
+        keys_tmp[best] = tk;
+        buf[best] = tb;
     }
+    return keys_tmp[k - 1];
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(const TensorScanArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const u32 S = a.stages, K = a.k_pad, KB = a.KB;
-    // [ring: S * 8 KiB (1024-byte aligned: swizzle atoms) | class maxima: k_pad*128*4 |
-    //  norms + inverse norms: 2 * 2*64*4 | survivor counts: 128*4 | barriers | tmem base]
+    const u32 S = a.stages, KB = a.KB, SKB = a.stage_kb;
+    const u32 stage_bytes = SKB * kTileBytes;
+    // [ring: S stages (1024-byte aligned: swizzle atoms) | norm ring: 16 x (64 |a| + 64 1/|a|) |
+    //  barriers | tmem base]
     unsigned char* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    float* s_gm = reinterpret_cast<float*>(ring + (size_t)S * kTileBytes);  // gm[class*128 + q]
-    float* s_na = s_gm + (size_t)K * kTcQ;
-    float* s_inv = s_na + 2 * kTcN;
-    u32* s_cnt = reinterpret_cast<u32*>(s_inv + 2 * kTcN);
-    u64* bars = reinterpret_cast<u64*>(s_cnt + kTcQ);
-    u64* full_bar = bars;               // [S]   TMA -> MMA
-    u64* empty_bar = bars + S;          // [S]   MMA -> TMA
-    u64* accf_bar = bars + 2 * S;       // [2]   MMA -> epilogue
-    u64* acce_bar = bars + 2 * S + 2;   // [2]   epilogue -> MMA
-    u64* aready_bar = bars + 2 * S + 4; // [1]   queries are in TMEM
-    u32* s_tmem = reinterpret_cast<u32*>(bars + 2 * S + 5);
+    float* s_norm = reinterpret_cast<float*>(ring + (size_t)S * stage_bytes);  // [slot][0:64 |a|, 64:128 1/|a|]
+    u64* bars = reinterpret_cast<u64*>(s_norm + kTcNormSlots * 2 * kTcN);
+    u64* full_bar = bars;                 // [S]   TMA -> MMA
+    u64* empty_bar = bars + S;            // [S]   MMA -> TMA
+    u64* accf_bar = bars + 2 * S;         // [2]   MMA -> epilogue
+    u64* acce_bar = bars + 2 * S + 2;     // [2]   epilogue -> MMA
+    u64* aready_bar = bars + 2 * S + 4;   // [1]   queries are in TMEM
+    u64* nfull_bar = bars + 2 * S + 5;                     // [kTcNormSlots] TMA -> epilogue (norm blocks)
+    u64* nempty_bar = bars + 2 * S + 5 + kTcNormSlots;     // [kTcNormSlots] epilogue -> TMA
+    u32* s_tmem = reinterpret_cast<u32*>(bars + 2 * S + 5 + 2 * kTcNormSlots);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -197,6 +210,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
             mbar_init(smem_u32(acce_bar + i), kTcQ);
         }
         mbar_init(smem_u32(aready_bar), kTcQ);
+        for (u32 i = 0; i < kTcNormSlots; i++) {
+            mbar_init(smem_u32(nfull_bar + i), 1);
+            mbar_init(smem_u32(nempty_bar + i), kTcQ);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -225,11 +242,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
             for (u32 sq = 0; sq < n_seq; sq++) {
                 const u32 li = sq < my_tiles ? sq : sq - my_tiles;
                 const size_t tile = (size_t)blockIdx.x + (size_t)li * gridDim.x;
-                for (u32 kb = 0; kb < KB; kb++) {
+                {   // the tile's 64 norms and inverse norms (2 x 256 bytes)
+                    const u32 ns = sq % kTcNormSlots;
+                    mbar_wait(smem_u32(nempty_bar + ns), ((sq / kTcNormSlots) & 1) ^ 1);
+                    mbar_expect_tx(smem_u32(nfull_bar + ns), 2 * kTcN * sizeof(float));
+                    float* dst = s_norm + (size_t)ns * 2 * kTcN;
+                    bulk_g2s(smem_u32(dst), a.norms + tile * kTcN, kTcN * sizeof(float),
+                             smem_u32(nfull_bar + ns), policy);
+                    bulk_g2s(smem_u32(dst + kTcN), a.inv_norms + tile * kTcN, kTcN * sizeof(float),
+                             smem_u32(nfull_bar + ns), policy);
+                }
+                for (u32 kb0 = 0; kb0 < KB; kb0 += SKB) {  // one copy per stage (several column blocks)
+                    const u32 bytes = min(SKB, KB - kb0) * kTileBytes;
                     mbar_wait(smem_u32(empty_bar + slot), phase ^ 1);
-                    mbar_expect_tx(smem_u32(full_bar + slot), kTileBytes);
-                    bulk_g2s(smem_u32(ring + (size_t)slot * kTileBytes), a.tiles + (tile * KB + kb) * kTileBytes,
-                             kTileBytes, smem_u32(full_bar + slot), policy);
+                    mbar_expect_tx(smem_u32(full_bar + slot), bytes);
+                    bulk_g2s(smem_u32(ring + (size_t)slot * stage_bytes), a.tiles + (tile * KB + kb0) * kTileBytes,
+                             bytes, smem_u32(full_bar + slot), policy);
                     if (++slot == S) {
                         slot = 0;
                         phase ^= 1;
@@ -248,14 +276,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
                 mbar_wait(smem_u32(acce_bar + buf), ((li >> 1) & 1) ^ 1);  // epilogue drained this accumulator
                 tc_fence_after();
                 const u32 d_tmem = tmem + buf * kTcN;
-                for (u32 kb = 0; kb < KB; kb++) {
+                for (u32 kb0 = 0; kb0 < KB; kb0 += SKB) {
                     mbar_wait(smem_u32(full_bar + slot), phase);
                     tc_fence_after();
-                    const u64 desc = make_sw128_desc(smem_u32(ring + (size_t)slot * kTileBytes));
+                    const u32 nkb = min(SKB, KB - kb0);
+                    for (u32 kk = 0; kk < nkb; kk++) {
+                        const u32 kb = kb0 + kk;
+                        const u64 desc = make_sw128_desc(smem_u32(ring + (size_t)slot * stage_bytes + (size_t)kk * kTileBytes));
 #pragma unroll
-                    for (u32 k4 = 0; k4 < 4; k4++)  // 4 x K16 per 64-column block
-                        tc_mma_ts(d_tmem, tmem_a + (kb * 4 + k4) * 8, desc + (u64)(k4 * 2), kIdescBf16M128N64,
-                                  (kb | k4) != 0 ? 1u : 0u);
+                        for (u32 k4 = 0; k4 < 4; k4++)  // 4 x K16 per 64-column block
+                            tc_mma_ts(d_tmem, tmem_a + (kb * 4 + k4) * 8, desc + (u64)(k4 * 2), kIdescBf16M128N64,
+                                      (kb | k4) != 0 ? 1u : 0u);
+                    }
                     tc_commit(smem_u32(empty_bar + slot));  // slot reusable once these MMAs retire
                     if (++slot == S) {
                         slot = 0;
@@ -272,13 +304,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
         const float* qp = a.queries + (size_t)(active ? q : 0) * a.dim;
         const u32 lane_addr = ((u32)(warp * 32) << 16);
         float qsq = 0.0f;
+        const bool vec_ok = (a.dim % 4 == 0) && ((reinterpret_cast<size_t>(qp) & 15) == 0);
         for (u32 cb = 0; cb < KB * 2; cb++) {  // 32 elements -> 16 packed columns per store
+            float f[32];
+            if (vec_ok && active && cb * 32 + 32 <= a.dim) {
+                const float4* q4 = reinterpret_cast<const float4*>(qp + cb * 32);
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const float4 t4 = q4[e];
+                    f[4 * e] = t4.x; f[4 * e + 1] = t4.y; f[4 * e + 2] = t4.z; f[4 * e + 3] = t4.w;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 32; e++) {
+                    const u32 c = cb * 32 + e;
+                    f[e] = (active && c < a.dim) ? qp[c] : 0.0f;
+                }
+            }
             u32 r[16];
 #pragma unroll
             for (int e = 0; e < 16; e++) {
-                const u32 c = cb * 32 + 2 * e;
-                const unsigned short lo = (active && c < a.dim) ? f32_to_bf16_rne(qp[c]) : 0;
-                const unsigned short hi = (active && c + 1 < a.dim) ? f32_to_bf16_rne(qp[c + 1]) : 0;
+                const unsigned short lo = f32_to_bf16_rne(f[2 * e]), hi = f32_to_bf16_rne(f[2 * e + 1]);
                 const float flo = __uint_as_float((u32)lo << 16), fhi = __uint_as_float((u32)hi << 16);
                 qsq = __fadd_rn(qsq, __fmul_rn(flo, flo));  // |b| over the rounded query, sequential
                 qsq = __fadd_rn(qsq, __fmul_rn(fhi, fhi));
@@ -290,19 +336,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
         tc_fence_before();
         mbar_arrive(smem_u32(aready_bar));
         const float mag_b = __fsqrt_rn(qsq);
-        const u32 k = a.k;
         // The identity shortcut (src/metrics.rs:148-151) precedes every other rule.  Two vectors
         // within 1e-10 per element have sim ~ 1 unless the query itself is tiny (|b| < 1e-6): such
         // a query is never pruned and checks every row exactly.
         const bool tiny_q = !(mag_b >= 1e-6f);
 
-        float* gm = s_gm + q;  // my class maxima: gm[class * 128]
-        for (u32 g = 0; g < k; g++) gm[(size_t)g * kTcQ] = -INFINITY;
-        u32* g_gm = a.g_gm + (size_t)q * k;
-        SurvivorState surv;
-        surv.buf = a.survivors + ((size_t)q * gridDim.x + blockIdx.x) * kTcSurvivorCap;
-        surv.cnt = 0;
-        surv.tau_exact = kKeyMax;
+        // classes: (row position in its tile) x (CTA group); this CTA owns 64 of the kc classes
+        const u32 T = (a.k + kTcN - 1) / kTcN, kc = T * kTcN;
+        const u32 group = blockIdx.x % T;
+        u32* g_gm = a.g_gm + q;  // class c of my query: g_gm[c * 128]  (a warp touches 128 contiguous bytes)
+        float gmr[kTcN];  // my 64 class maxima, in registers
+#pragma unroll
+        for (u32 j = 0; j < kTcN; j++) gmr[j] = -INFINITY;
+
+        // survivor slots of this (CTA, query): the upper half doubles as scratch for a compaction
+        u64* surv_buf = a.survivors + ((size_t)q * gridDim.x + blockIdx.x) * (2 * kTcSurvivorCap);
+        u32 surv_cnt = 0;
         float thr = -INFINITY;    // prune rows with t < thr, t = S / |a|
 
         for (u32 sq = 0; sq < n_seq; sq++) {
@@ -311,12 +360,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
             const bool learn_only = sq < learn;
             const u32 tile = blockIdx.x + li * gridDim.x;
             const u32 row0 = tile * kTcN;
-            if (q < kTcN) {
-                const float na = (row0 + q < a.n_rows) ? __ldg(a.norms + row0 + q) : 0.0f;
-                s_na[buf * kTcN + q] = na;
-                s_inv[buf * kTcN + q] = (na > 0.0f) ? __fdiv_rn(1.0f, na) : 0.0f;  // NaN/0 -> 0: handled exactly below
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
+            const u32 ns = sq % kTcNormSlots;
+            const float* na_s = s_norm + (size_t)ns * 2 * kTcN;
+            const float4* inv4 = reinterpret_cast<const float4*>(na_s + kTcN);
 
             mbar_wait(smem_u32(accf_bar + buf), (sq >> 1) & 1);
             tc_fence_after();
@@ -326,85 +372,109 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
             mbar_arrive(smem_u32(acce_bar + buf));  // scores are in registers: free the accumulator
+            mbar_wait(smem_u32(nfull_bar + ns), (sq / kTcNormSlots) & 1);
 
+            u32 mask_lo = 0, mask_hi = 0;  // my survivors of this tile (bit j = score j)
             if (active) {
                 const u32 n_here = min(kTcN, a.n_rows - row0);
-                u32 g = row0 % k;  // residue class of the tile's first row
-                // pass 1 (branch-free, unrolled): class maxima and a bit mask of the survivors
-                const float* inv = s_inv + buf * kTcN;
+                // pass 1 -- branch-free and unrolled, so the 64 independent chains overlap: one multiply,
+                // one FMNMX, one compare per score, survivors recorded in a 64-bit mask
                 const float pass_thr = learn_only ? INFINITY : thr;
                 u32 m_lo = 0, m_hi = 0;
 #pragma unroll
-                for (u32 j = 0; j < kTcN; j++) {
-                    // rows past the end of the store have inv == 0 and score 0: they can only raise a
-                    // class maximum to 0, never above a real row's, and are masked out below
-                    const float t = v[j] * inv[j];
-                    float* cell = gm + (size_t)g * kTcQ;
-                    *cell = fmaxf(*cell, j < n_here ? t : -INFINITY);  // a NaN score leaves the maximum untouched
-                    const u32 bit = (!(t < pass_thr)) ? 1u : 0u;
-                    if (j < 32) m_lo |= bit << (j & 31);
-                    else m_hi |= bit << (j & 31);
-                    g = (g + 1 == k) ? 0 : g + 1;
+                for (u32 j4 = 0; j4 < kTcN / 4; j4++) {
+                    const float4 iv = inv4[j4];
+                    const float ivs[4] = {iv.x, iv.y, iv.z, iv.w};
+#pragma unroll
+                    for (u32 e = 0; e < 4; e++) {
+                        const u32 j = j4 * 4 + e;
+                        const float t = v[j] * ivs[e];
+                        // rows past the end of the store never count; a NaN score leaves the maximum alone
+                        gmr[j] = fmaxf(gmr[j], j < n_here ? t : -INFINITY);
+                        const u32 bit = (!(t < pass_thr)) ? 1u : 0u;
+                        if (j < 32) m_lo |= bit << (j & 31);
+                        else m_hi |= bit << (j & 31);
+                    }
                 }
                 if (n_here < kTcN) {  // last tile of the store: drop the padding rows
                     const u64 keep = (1ull << n_here) - 1ull;
                     m_lo &= (u32)keep;
                     m_hi &= (u32)(keep >> 32);
                 }
-                if (learn_only) m_lo = m_hi = 0;
-                // pass 2 (rare): exact distance for the survivors
-                if (m_lo | m_hi) {
-#pragma unroll
-                    for (u32 j = 0; j < kTcN; j++) {
-                        if (((j < 32 ? m_lo : m_hi) >> (j & 31)) & 1u)
-                            tc_survivor(surv, a, qp, row0 + j, v[j], s_na[buf * kTcN + j], mag_b, tiny_q);
+                mask_lo = m_lo;
+                mask_hi = m_hi;
+            }
+            // pass 2 -- visit only the score positions where SOME lane of the warp has a survivor
+            // (about two per tile): a jump table picks the register, the owning lanes append
+            {
+                u32 w_lo = __reduce_or_sync(0xFFFFFFFFu, mask_lo), w_hi = __reduce_or_sync(0xFFFFFFFFu, mask_hi);
+                while (w_lo | w_hi) {
+                    u32 j;
+                    if (w_lo) {
+                        j = __ffs(w_lo) - 1;
+                        w_lo &= w_lo - 1;
+                    } else {
+                        j = 32 + __ffs(w_hi) - 1;
+                        w_hi &= w_hi - 1;
                     }
-                }
-                // the bound improves like log(rows seen): refresh densely while it is young, then
-                // every 8 / 32 / 128 tiles
-                const u32 every = sq < 64 ? 8u : (sq < 512 ? 32u : 128u);
-                const bool refresh = (sq + 1 == learn) || (sq >= learn && sq < learn + 8) || ((sq + 1) % every == 0);
-                if (refresh && !tiny_q) {
-                    float bound = INFINITY;
-                    for (u32 c0 = 0; c0 < k; c0 += 32) {
-                        u32 their_bits[32];  // 32 independent L2 reads in flight, then the merge
-#pragma unroll
-                        for (u32 i = 0; i < 32; i++) their_bits[i] = (c0 + i < k) ? __ldcg(g_gm + c0 + i) : 0u;
-#pragma unroll
-                        for (u32 i = 0; i < 32; i++) {
-                            if (c0 + i < k) {
-                                float mine = gm[(size_t)(c0 + i) * kTcQ];
-                                // 0 = nobody has published this class yet
-                                const float theirs = their_bits[i] ? f32_from_ordered(their_bits[i]) : -INFINITY;
-                                if (mine > theirs) atomicMax(g_gm + c0 + i, f32_ordered(mine));
-                                else if (theirs > mine) gm[(size_t)(c0 + i) * kTcQ] = mine = theirs;
-                                bound = fminf(bound, mine);
-                            }
+                    float sc;
+                    switch (j) {
+#define BSR_CASE(J) case J: sc = v[J]; break;
+#define BSR_CASE8(B) BSR_CASE(B) BSR_CASE(B + 1) BSR_CASE(B + 2) BSR_CASE(B + 3) BSR_CASE(B + 4) BSR_CASE(B + 5) BSR_CASE(B + 6) BSR_CASE(B + 7)
+                        BSR_CASE8(0) BSR_CASE8(8) BSR_CASE8(16) BSR_CASE8(24) BSR_CASE8(32) BSR_CASE8(40) BSR_CASE8(48)
+                        BSR_CASE8(56)
+#undef BSR_CASE8
+#undef BSR_CASE
+                        default: sc = 0.0f; break;
+                    }
+                    if (((j < 32 ? mask_lo : mask_hi) >> (j & 31)) & 1u) {
+                        surv_buf[surv_cnt++] = pack_survivor(row0 + j, sc);
+                        if (surv_cnt == kTcSurvivorCap) {
+                            // overflow (adversarial row order only): keep the exact best k
+                            compact_survivors(a, surv_buf, surv_cnt, qp, mag_b, surv_buf + kTcSurvivorCap);
+                            surv_cnt = a.k;
                         }
                     }
-                    // k distinct rows reach `bound`; keep a 1e-6 (in similarity) safety margin
+                }
+            }
+            mbar_arrive(smem_u32(nempty_bar + ns));  // norm block consumed
+
+            if (active && !tiny_q) {
+                // merge my class maxima with everyone else's and refresh the bound.  The bound improves
+                // like log(rows seen): refresh densely while it is young, then every 8 / 32 / 128 tiles
+                const u32 every = sq < 64 ? 8u : (sq < 512 ? 32u : 128u);
+                const bool refresh = (sq + 1 == learn) || (sq >= learn && sq < learn + 8) || ((sq + 1) % every == 0);
+                if (refresh) {
+                    float bound = INFINITY;
+                    for (u32 c0 = 0; c0 < kc; c0 += kTcN) {  // one 64-class group at a time
+                        u32 their_bits[kTcN];
+#pragma unroll
+                        for (u32 i = 0; i < kTcN; i++) their_bits[i] = __ldcg(g_gm + (size_t)(c0 + i) * kTcQ);  // independent, coalesced L2 reads
+                        const bool mine_group = (c0 == group * kTcN);
+#pragma unroll
+                        for (u32 i = 0; i < kTcN; i++) {
+                            // 0 = nobody has published this class yet
+                            float best = their_bits[i] ? f32_from_ordered(their_bits[i]) : -INFINITY;
+                            if (mine_group) {
+                                if (gmr[i] > best) {
+                                    atomicMax(g_gm + (size_t)(c0 + i) * kTcQ, f32_ordered(gmr[i]));
+                                    best = gmr[i];
+                                } else {
+                                    gmr[i] = best;
+                                }
+                            }
+                            bound = fminf(bound, best);
+                        }
+                    }
+                    // kc >= k distinct rows reach `bound`; keep a 1e-6 (in similarity) safety margin
                     thr = (bound == -INFINITY) ? -INFINITY : bound - 1e-6f * mag_b - 1e-6f * fabsf(bound);
                 }
             }
         }
-        s_cnt[q] = active ? surv.cnt : 0;
-        __threadfence_block();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        // every warp sorts the survivors of its queries in the (now idle) ring and writes the best K
-        {
-            u64* scratch = reinterpret_cast<u64*>(ring) + (size_t)warp * kTcSurvivorCap;
-            for (u32 qq = warp; qq < a.nq_valid; qq += 4) {
-                const u32 n = s_cnt[qq];
-                u32 P = K;
-                while (P < n) P <<= 1;
-                const u64* src = a.survivors + ((size_t)qq * gridDim.x + blockIdx.x) * kTcSurvivorCap;
-                for (u32 j = lane; j < P; j += 32) scratch[j] = j < n ? src[j] : kKeyMax;
-                __syncwarp();
-                warp_sort_list(scratch, P, lane);
-                u64* out = a.cta_keys + ((size_t)qq * gridDim.x + blockIdx.x) * K;
-                for (u32 j = lane; j < K; j += 32) out[j] = scratch[j];
-                __syncwarp();
-            }
+        // exact keys + sort of the survivors happen in finalize_survivors_kernel (fully parallel)
+        if (active) {
+            a.surv_count[(size_t)q * gridDim.x + blockIdx.x] = surv_cnt;
+            if (blockIdx.x == 0) a.q_mag[q] = mag_b;
         }
     }
 
@@ -415,6 +485,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
     }
+}
+
+// One warp per (query, CTA) survivor list: raw (row, score) pairs -> exact keys (the reference's
+// distance formula) -> bitonic sort -> the best k_pad written as an ascending candidate list.
+__global__ void __launch_bounds__(256) finalize_survivors_kernel(const TensorScanArgs a, u32 n_cta) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64* scratch = reinterpret_cast<u64*>(smem_raw) + (size_t)warp * kTcSurvivorCap;
+    const u32 list = blockIdx.x * (blockDim.x >> 5) + warp;  // = q * n_cta + cta
+    if (list >= a.nq_valid * n_cta) return;
+    const u32 q = list / n_cta;
+    const u32 K = a.k_pad;
+    const u32 n = min(a.surv_count[list], kTcSurvivorCap);
+    u32 P = K;
+    while (P < n) P <<= 1;
+    const u64* src = a.survivors + (size_t)list * (2 * kTcSurvivorCap);
+    const float* qp = a.queries + (size_t)q * a.dim;
+    const float mag_b = a.q_mag[q];
+    for (u32 j = lane; j < P; j += 32) scratch[j] = j < n ? survivor_key(a, src[j], qp, mag_b) : kKeyMax;
+    __syncwarp();
+    warp_sort_list(scratch, P, lane);
+    u64* out = a.cta_keys + (size_t)list * K;
+    for (u32 j = lane; j < K; j += 32) out[j] = scratch[j];
 }
 
 }  // namespace bsr
