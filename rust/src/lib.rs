@@ -53,6 +53,10 @@ pub mod ffi {
                                  top_k: u32, d_idx: *mut u64, d_dist: *mut f32, d_count: *mut u32,
                                  stream: *mut c_void) -> c_int;
 
+        pub fn bsr_merge_host(store: *mut bsr_store, idx: *const u64, dist: *const f32, n: u64,
+                              top_k: u32, out_idx: *mut u64, out_dist: *mut f32,
+                              out_count: *mut u32) -> c_int;
+        pub fn bsr_store_set_tensor_min_batch(store: *mut bsr_store, min_batch: u32) -> c_int;
         pub fn bsr_store_launch_count(store: *const bsr_store, n_launches: *mut u64) -> c_int;
         pub fn bsr_store_last_scan_ms(store: *mut bsr_store, ms: *mut f32) -> c_int;
         pub fn bsr_store_set_profiling(store: *mut bsr_store, enabled: c_int) -> c_int;
@@ -197,6 +201,25 @@ impl GpuVectorstore {
         })?;
         Ok((0..count as usize).map(|i| (idx[i] as usize, dist[i])).collect())
     }
+}
+
+/// `compute_global_top_k` (src/mpi_helpers/metrics.rs:141-171): the gathered pairs are sorted by
+/// (distance, index) on the GPU; `scratch` is any store handle on the device that should do it.
+pub fn compute_global_top_k(scratch: &mut GpuVectorstore, global_indices: Vec<usize>,
+                            global_distances: Vec<f32>, top_k: usize)
+    -> Result<Vec<(usize, f32)>, BsrError> {
+    if global_indices.is_empty() {
+        return Ok(vec![]);
+    }
+    let gi: Vec<u64> = global_indices.iter().map(|&i| i as u64).collect();
+    let mut idx = vec![0u64; top_k];
+    let mut dist = vec![0f32; top_k];
+    let mut count = 0u32;
+    check(unsafe {
+        ffi::bsr_merge_host(scratch.handle, gi.as_ptr(), global_distances.as_ptr(), gi.len() as u64,
+                            top_k as u32, idx.as_mut_ptr(), dist.as_mut_ptr(), &mut count)
+    })?;
+    Ok((0..count as usize).map(|i| (idx[i] as usize, dist[i])).collect())
 }
 
 impl Drop for GpuVectorstore {
