@@ -1,0 +1,89 @@
+"""Runs the BASELINE.json configurations that fit one GPU and prints one JSON object
+(gpurun_out/r01_configs.json).  Device-side numbers use CUDA events on the launching stream."""
+import json
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+import better_search_rag_rust_b200 as bsr  # noqa: E402
+from oracle import c_oracle as co  # noqa: E402
+
+SEED = 0x5EED0001
+out = {}
+
+
+def timed(fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def single_query(name, n, k, dtype="f32", reps=200, cpu=False):
+    st = bsr.GpuVectorstore(None, True, dim=768, capacity_rows=n, dtype=dtype)
+    st.append_synthetic(SEED, 0, n)
+    eng = bsr.CudaShardEngine(st)
+    q_np = st.get(0)
+    q = torch.from_numpy(q_np).cuda().reshape(1, -1)
+    cand = torch.empty((1, bsr.candidate_slots(k)), dtype=torch.int64, device="cuda")
+    st.set_profiling(True)
+    ms = timed(lambda: eng.search_candidates(q, k, out=cand), reps)
+    scan_ms, n_scans = st.scan_profile()
+    st.set_profiling(False)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        idx, dist, cnt = eng.local_top_k(q_np, k)
+    e2e_ms = (time.perf_counter() - t0) / reps * 1e3
+    assert idx[0, 0] == 0 and dist[0, 0] == 0.0
+    r = {"rows": n, "dtype": dtype, "k": k, "ms_per_query": ms, "queries_per_s": 1e3 / ms,
+         "scan_kernel_ms": scan_ms / n_scans, "scan_GBps": st.scan_bytes() / (scan_ms / n_scans) / 1e6,
+         "e2e_ms_per_query": e2e_ms, "e2e_queries_per_s": 1e3 / e2e_ms}
+    if cpu:
+        rows = co.generate_rows(SEED, 0, n, 768)
+        for threads in (1, 16):
+            t0 = time.perf_counter()
+            reps_c = 3
+            for _ in range(reps_c):
+                co.parallel_top_k_similarity_search(rows, threads, k, rows[0], n_threads=threads)
+            r[f"cpu_oracle_ms_per_query_{threads}_ranks"] = (time.perf_counter() - t0) / reps_c * 1e3
+    out[name] = r
+    st.close()
+    print(name, json.dumps(r), flush=True)
+
+
+def batches(name, n, k, dtype, sizes, reps=3):
+    st = bsr.GpuVectorstore(None, True, dim=768, capacity_rows=n, dtype=dtype)
+    st.append_synthetic(SEED, 0, n)
+    eng = bsr.CudaShardEngine(st)
+    res = []
+    for nq in sizes:
+        qs = torch.from_numpy(co.generate_rows(SEED + 0x1000, 0, nq, 768)).cuda()
+        cand = torch.empty((nq, bsr.candidate_slots(k)), dtype=torch.int64, device="cuda")
+        ms = timed(lambda: eng.search_candidates(qs, k, out=cand), max(reps, 64 // nq), warm=2)
+        res.append({"queries": nq, "ms_per_batch": ms, "queries_per_s": nq / ms * 1e3,
+                    "TFLOPs": 2.0 * n * 768 * nq / ms / 1e9})
+    out[name] = {"rows": n, "dtype": dtype, "k": k, "sweep": res}
+    st.close()
+    print(name, json.dumps(out[name]), flush=True)
+
+
+single_query("config0_50k_fp32_k10", 50_000, 10, cpu=True)
+single_query("config0b_50k_fp32_k50_reference_k", 50_000, 50)
+single_query("config1_1M_fp32_k10", 1_000_000, 10)
+single_query("config4_shard_12.5M_fp32_k10", 12_500_000, 10, reps=50)
+single_query("extra_1M_bf16_k10_exact", 1_000_000, 10, dtype="bf16")
+for k in (1, 50, 100, 256, 1024):
+    single_query(f"config5_ksweep_1M_fp32_k{k}", 1_000_000, k, reps=100)
+batches("config5_batch_sweep_1M_fp32_exact_k10", 1_000_000, 10, "f32", [1, 2, 4, 8, 64, 256])
+batches("config5_batch_sweep_1M_bf16_tensor_k10", 1_000_000, 10, "bf16", [32, 128, 1024, 4096])
+batches("config2_10M_bf16_tensor_k100", 10_000_000, 100, "bf16", [128, 1024])
+json.dump(out, open("gpurun_out/r01_configs.json", "w"), indent=1)
