@@ -195,10 +195,10 @@ def cpu_baseline(rows_per_query: int, top_k: int, budget_s: float = 12.0) -> dic
             "ms_per_query": sec * 1e3}
 
 
-def run_reference(args) -> None:
+def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     from oracle import c_oracle as co
     co.build()
     threads = _host_threads()
@@ -234,7 +234,7 @@ def run_reference(args) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    return line
 
 
 # ---------------------------------------------------------------------------------------------
@@ -262,7 +262,7 @@ def _traffic_per_launch(rows_per_gpu: int):
     return None
 
 
-def run_b200(args) -> None:
+def run_b200(args):
     import torch
     import torch.distributed as dist
 
@@ -375,7 +375,7 @@ def run_b200(args) -> None:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
-        return
+        return None
 
     # sanity: the self-query must come back first with distance exactly 0 (src/main.rs:148-154)
     if world == 1:
@@ -423,42 +423,28 @@ def run_b200(args) -> None:
         except Exception as e:  # the GPU numbers stand even if the host leg cannot run
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": _host_threads(),
                                     "kind": "port", "sample": f"failed: {e!r}"}
-    print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return line
 
 
 def main():
     args = parse_args()
-    # The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, torchrun
-    # notices) also write to fd 1, so everything except that line is sent to stderr.
+    # The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, torchrun notices)
+    # also write to fd 1, so while the benchmark runs fd 1 points at stderr; the line is written to
+    # the real stdout at the end.
     sys.stdout.flush()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
-    line_holder = []
-    import builtins
-    orig_print = builtins.print
-
-    def capture_print(*a, **kw):
-        if kw.get("file") in (None, sys.stdout) and len(a) == 1 and isinstance(a[0], str) and a[0].startswith("{"):
-            line_holder.append(a[0])
-        else:
-            orig_print(*a, **kw)
-
-    builtins.print = capture_print
     try:
-        if args.impl == "reference":
-            run_reference(args)
-        else:
-            run_b200(args)
+        line = run_reference(args) if args.impl == "reference" else run_b200(args)
     finally:
-        builtins.print = orig_print
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         os.close(real_stdout)
-    for line in line_holder:
-        print(line, flush=True)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
