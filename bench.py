@@ -310,10 +310,17 @@ def run_b200(args):
             if rank == 0:
                 eng.merge(gathered, k, out=merged)
 
+    comm = None
+    if world > 1:
+        # the library's own NCCL communicator: the id travels over the host channel (here torch's)
+        ids = [bsr.BsrComm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        comm = bsr.BsrComm(ids[0], world, rank, local)
+
     def step_e2e():
         if world == 1:
             return eng.local_top_k(q_np, k)  # bsr_search: host buffers in, host buffers out
-        return bsr.parallel_top_k_similarity_search(None, rank, world, None, k, q_np[0], engine=eng)
+        return comm.search(eng, q_np, k)     # bsr_search_parallel: one C-ABI call per rank
 
     def fence():
         torch.cuda.synchronize()
@@ -378,11 +385,8 @@ def run_b200(args):
         return None
 
     # sanity: the self-query must come back first with distance exactly 0 (src/main.rs:148-154)
-    if world == 1:
-        idx, dst, cnt = res
-        assert int(idx[0, 0]) == 0 and float(dst[0, 0]) == 0.0 and int(cnt[0]) == k, (idx, dst, cnt)
-    else:
-        assert res[0][0] == 0 and res[0][1] == 0.0 and len(res) == k, res
+    idx, dst, cnt = res
+    assert int(idx[0, 0]) == 0 and float(dst[0, 0]) == 0.0 and int(cnt[0]) == k, (idx, dst, cnt)
 
     peak, peak_src = _peak_gbs()
     scan_bytes = store.scan_bytes()
@@ -411,7 +415,7 @@ def run_b200(args):
                 "d2h_bytes_per_step": k * 12 + 4,
                 "ms_per_step": e2e_s / steps * 1e3,
                 "path": "bsr_search (C ABI, host buffers)" if world == 1 else
-                        "parallel_top_k_similarity_search (host query -> root's host top-k)"},
+                        "bsr_search_parallel (C ABI, host buffers: scan -> ncclAllGather -> merge on root)"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(t_wall0, t_wall1),
     }

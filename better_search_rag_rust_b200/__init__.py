@@ -10,7 +10,7 @@ from ._lib import BsrError, BSR_MAX_TOP_K, LIB_PATH  # noqa: F401
 from .load_balance import RankInterval, RankSlice, interval_by_rank, slice_by_rank  # noqa: F401
 from .metrics import (calculate_accuracy_metrics, format_accuracy_metrics,  # noqa: F401
                       format_top_k_results, print_top_k_results)
-from .search import (ROOT, CudaShardEngine, candidate_slots, compute_global_top_k,  # noqa: F401
+from .search import (ROOT, BsrComm, CudaShardEngine, candidate_slots, compute_global_top_k,  # noqa: F401
                      compute_local_top_k, gather_top_k_results, is_root, open_shard,
                      pack_candidates, parallel_top_k_similarity_search, release_shards,
                      unpack_candidates)

@@ -21,6 +21,7 @@ BSR_ERR_UNSUPPORTED = -5
 BSR_F32 = 0
 BSR_BF16 = 1
 BSR_MAX_TOP_K = 1024
+BSR_COMM_ID_BYTES = 128
 
 
 class BsrError(RuntimeError):
@@ -66,6 +67,11 @@ SIGNATURES = {
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "bsr_merge_host": (C.c_int, [_store, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p,
                                  C.c_void_p, _u32p]),
+    "bsr_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "bsr_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "bsr_comm_destroy": (C.c_int, [C.c_void_p]),
+    "bsr_search_parallel": (C.c_int, [_store, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
     "bsr_store_set_tensor_min_batch": (C.c_int, [_store, C.c_uint32]),
     "bsr_store_launch_count": (C.c_int, [_store, _u64p]),
     "bsr_store_last_scan_ms": (C.c_int, [_store, _f32p]),

@@ -1,6 +1,7 @@
 // bsr_api.cu -- host side of the C ABI declared in include/bsr.h.
 // Plain CUDA runtime; no torch types cross this boundary.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -73,7 +74,7 @@ struct bsr_store {
     size_t smem_optin = 0;
 
     // per-search scratch (grown on demand)
-    DevBuf cta_keys, merge_a, merge_b, d_queries, d_cand, d_result, d_counter, d_gtau, d_surv, staging;
+    DevBuf cta_keys, merge_a, merge_b, d_queries, d_cand, d_result, d_counter, d_gtau, d_surv, d_gather, staging;
     u32 tensor_min_batch = 32;  // BF16 stores: batches at least this large use the tcgen05 path (0 = never)
     void* h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
@@ -243,7 +244,7 @@ extern "C" int bsr_store_destroy(bsr_store* s) {
     DeviceGuard g(s->device);
     cudaStreamSynchronize(s->stream);
     DevBuf* bufs[] = {&s->cta_keys, &s->merge_a, &s->merge_b, &s->d_queries,
-                      &s->d_cand,   &s->d_result, &s->d_counter, &s->d_gtau, &s->d_surv, &s->staging};
+                      &s->d_cand,   &s->d_result, &s->d_counter, &s->d_gtau, &s->d_surv, &s->d_gather, &s->staging};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (s->panels) cudaFree(s->panels);
@@ -902,6 +903,152 @@ extern "C" int bsr_merge_host(bsr_store* s, const uint64_t* idx, const float* di
     memcpy(out_idx, h, (size_t)cnt * sizeof(u64));
     memcpy(out_dist, h + ibytes, (size_t)cnt * sizeof(float));
     *out_count = cnt;
+    return BSR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-rank search: NCCL resolved at run time
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct NcclId {
+    char internal[BSR_COMM_ID_BYTES];
+};
+struct NcclApi {
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+const int kNcclUint64 = 5;  // ncclDataType_t
+
+NcclApi& nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    // prefer the copy already mapped into the process (e.g. the one torch.distributed uses)
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return api;
+    api.GetUniqueId = (int (*)(NcclId*))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+    api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+    api.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy;
+    return api;
+}
+}  // namespace
+
+struct bsr_comm {
+    void* comm = nullptr;
+    int n_ranks = 0, rank = 0, device = 0;
+};
+
+#define NCCL(expr)                                                                              \
+    do {                                                                                        \
+        int r_ = (expr);                                                                        \
+        if (r_ != 0)                                                                            \
+            return fail(BSR_ERR_CUDA, "%s failed: %s", #expr,                                   \
+                        nccl().GetErrorString ? nccl().GetErrorString(r_) : "NCCL error");      \
+    } while (0)
+
+extern "C" int bsr_comm_unique_id(uint8_t id[BSR_COMM_ID_BYTES]) {
+    CHECK(id, BSR_ERR_INVALID, "bsr_comm_unique_id: null output");
+    CHECK(nccl().ok, BSR_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded: %s", dlerror() ? dlerror() : "not found");
+    NcclId nid;
+    NCCL(nccl().GetUniqueId(&nid));
+    memcpy(id, nid.internal, BSR_COMM_ID_BYTES);
+    return BSR_OK;
+}
+
+extern "C" int bsr_comm_create(const uint8_t id[BSR_COMM_ID_BYTES], int n_ranks, int rank, int device,
+                               bsr_comm** out) {
+    CHECK(out, BSR_ERR_INVALID, "bsr_comm_create: null output");
+    *out = nullptr;
+    CHECK(id && n_ranks >= 1 && rank >= 0 && rank < n_ranks, BSR_ERR_INVALID, "bsr_comm_create: bad arguments");
+    CHECK(nccl().ok, BSR_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+    DeviceGuard g(device);
+    bsr_comm* c = new (std::nothrow) bsr_comm();
+    CHECK(c, BSR_ERR_OOM, "bsr_comm_create: host allocation failed");
+    c->n_ranks = n_ranks;
+    c->rank = rank;
+    c->device = device;
+    NcclId nid;
+    memcpy(nid.internal, id, BSR_COMM_ID_BYTES);
+    int r = nccl().CommInitRank(&c->comm, n_ranks, nid, rank);
+    if (r != 0) {
+        delete c;
+        return fail(BSR_ERR_CUDA, "ncclCommInitRank failed: %s",
+                    nccl().GetErrorString ? nccl().GetErrorString(r) : "NCCL error");
+    }
+    *out = c;
+    return BSR_OK;
+}
+
+extern "C" int bsr_comm_destroy(bsr_comm* c) {
+    if (!c) return BSR_OK;
+    DeviceGuard g(c->device);
+    if (c->comm) nccl().CommDestroy(c->comm);
+    delete c;
+    return BSR_OK;
+}
+
+extern "C" int bsr_search_parallel(bsr_store* s, bsr_comm* c, const float* queries, uint32_t nq, uint32_t k,
+                                   uint64_t* out_idx, float* out_dist, uint32_t* out_count) {
+    TRY(check_search_args(s, queries, nq, k, "bsr_search_parallel"));
+    CHECK(c && c->comm, BSR_ERR_INVALID, "bsr_search_parallel: null communicator");
+    CHECK(c->device == s->device, BSR_ERR_INVALID, "bsr_search_parallel: shard and communicator are on different devices");
+    const bool root = c->rank == 0;
+    if (nq == 0) return BSR_OK;
+    CHECK(!root || (out_idx && out_dist && out_count), BSR_ERR_INVALID, "bsr_search_parallel: null output on root");
+    DeviceGuard g(s->device);
+    const u32 K = bsr_candidate_slots(k);
+    const size_t qbytes = (size_t)nq * s->dim * sizeof(float);
+    const size_t ibytes = (size_t)nq * k * sizeof(u64), dbytes = (size_t)nq * k * sizeof(float),
+                 cbytes = (size_t)nq * sizeof(u32);
+    const size_t rbytes = ibytes + dbytes + cbytes, off_r = (qbytes + 15) & ~(size_t)15;
+    const size_t cand_bytes = (size_t)nq * K * sizeof(u64);
+    TRY(ensure_pinned(s, off_r + rbytes));
+    TRY(ensure(s->d_queries, qbytes));
+    TRY(ensure(s->d_cand, cand_bytes));
+    TRY(ensure(s->d_gather, cand_bytes * c->n_ranks + cand_bytes));
+    TRY(ensure(s->d_result, rbytes));
+    char* h = (char*)s->h_pinned;
+    memcpy(h, queries, qbytes);
+    CU(cudaMemcpyAsync(s->d_queries.p, h, qbytes, cudaMemcpyHostToDevice, s->stream));
+    if (s->n_rows == 0) {
+        // an empty shard contributes an empty list (metrics.rs:185-191): all slots UINT64_MAX
+        CU(cudaMemsetAsync(s->d_cand.p, 0xFF, cand_bytes, s->stream));
+    } else {
+        TRY(search_device_impl(s, (const float*)s->d_queries.p, nq, k, (u64*)s->d_cand.p, nullptr, nullptr,
+                               nullptr, s->stream));
+    }
+    // rank-ordered concatenation of every rank's [nq][K] slots (displacements, metrics.rs:86-89)
+    NCCL(nccl().AllGather(s->d_cand.p, s->d_gather.p, (size_t)nq * K, kNcclUint64, c->comm, s->stream));
+    if (root) {
+        u64* merged = (u64*)((char*)s->d_gather.p + cand_bytes * c->n_ranks);
+        const u32 max_per_cta = std::max<u32>(2, kMergeMaxKeys / K);
+        const size_t inter = (size_t)nq * ((c->n_ranks + max_per_cta - 1) / max_per_cta) * K * sizeof(u64);
+        TRY(ensure(s->merge_a, inter));
+        TRY(ensure(s->merge_b, inter));
+        TRY(merge_tree(s, (const u64*)s->d_gather.p, (u32)c->n_ranks, nq, K, (size_t)nq * K, K, merged, s->stream));
+        char* r = (char*)s->d_result.p;
+        unpack_kernel<<<nq, 128, 0, s->stream>>>(merged, K, k, (u64*)r, (float*)(r + ibytes),
+                                                 (u32*)(r + ibytes + dbytes));
+        s->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(h + off_r, r, rbytes, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    if (root) {
+        memcpy(out_idx, h + off_r, ibytes);
+        memcpy(out_dist, h + off_r + ibytes, dbytes);
+        memcpy(out_count, h + off_r + ibytes + dbytes, cbytes);
+    }
     return BSR_OK;
 }
 

@@ -211,6 +211,48 @@ inline std::optional<TopK> parallel_top_k_similarity_search(Communicator& world,
     return compute_global_top_k(shard, gi, gd, top_k);
 }
 
+// ---- the same with the library's own NCCL communicator (bsr_comm_*): scan, all-gather of the
+//      candidate slots over NVLink, on-device merge -- one C-ABI call per rank -------------------------
+class DeviceWorld {
+  public:
+    // rank 0 creates the id; ship the 128 bytes to every rank over the host's channel
+    static std::vector<uint8_t> unique_id() {
+        std::vector<uint8_t> id(BSR_COMM_ID_BYTES);
+        check(bsr_comm_unique_id(id.data()));
+        return id;
+    }
+    DeviceWorld(const std::vector<uint8_t>& id, int n_ranks, int rank, int device) : rank_(rank), size_(n_ranks) {
+        if (id.size() != BSR_COMM_ID_BYTES) throw Error(BSR_ERR_INVALID, "unique id must be 128 bytes");
+        check(bsr_comm_create(id.data(), n_ranks, rank, device, &c_));
+    }
+    ~DeviceWorld() { bsr_comm_destroy(c_); }
+    DeviceWorld(const DeviceWorld&) = delete;
+    DeviceWorld& operator=(const DeviceWorld&) = delete;
+    int rank() const { return rank_; }
+    int size() const { return size_; }
+    bsr_comm* handle() const { return c_; }
+
+  private:
+    bsr_comm* c_ = nullptr;
+    int rank_, size_;
+};
+
+inline std::optional<TopK> parallel_top_k_similarity_search(DeviceWorld& world, int rank, int /*size*/,
+                                                            GpuVectorstore& shard, size_t top_k,
+                                                            const std::vector<float>& target_vector) {
+    if (target_vector.size() != shard.dim()) throw Error(BSR_ERR_INVALID, "query length differs from the store");
+    std::vector<uint64_t> idx(top_k);
+    std::vector<float> dist(top_k);
+    uint32_t count = 0;
+    check(bsr_search_parallel(shard.handle(), world.handle(), target_vector.data(), 1, (uint32_t)top_k,
+                              is_root(rank) ? idx.data() : nullptr, is_root(rank) ? dist.data() : nullptr,
+                              is_root(rank) ? &count : nullptr));
+    if (!is_root(rank)) return std::nullopt;
+    TopK out;
+    for (uint32_t i = 0; i < count; i++) out.emplace_back((size_t)idx[i], dist[i]);
+    return out;
+}
+
 // ---- src/mpi_helpers/metrics.rs:209-249 --------------------------------------------------------------
 inline void print_top_k_results(const TopK& r) {
     std::printf("Global top-%zu results:\n", r.size());

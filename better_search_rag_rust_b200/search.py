@@ -165,6 +165,50 @@ class CudaShardEngine:
                 count.cpu().numpy().view(np.uint32))
 
 
+class BsrComm:
+    """A communicator owned by libbsr_b200.so (NCCL resolved inside the library): the `world` for
+    hosts that have no GPU communicator of their own.  Rank 0 calls `BsrComm.unique_id()` and ships
+    the 128 bytes to every rank over any host channel (the reference would MPI_Bcast them)."""
+
+    def __init__(self, unique_id: bytes, n_ranks: int, rank: int, device: int):
+        if len(unique_id) != _lib.BSR_COMM_ID_BYTES:
+            raise ValueError("unique_id must be 128 bytes")
+        self.n_ranks, self.rank, self.device = n_ranks, rank, device
+        self._id = (C.c_ubyte * _lib.BSR_COMM_ID_BYTES).from_buffer_copy(unique_id)
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib().bsr_comm_create(self._id, n_ranks, rank, device, C.byref(self._h)))
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_ubyte * _lib.BSR_COMM_ID_BYTES)()
+        _lib.check(_lib.lib().bsr_comm_unique_id(buf))
+        return bytes(buf)
+
+    def search(self, engine: "CudaShardEngine", queries, top_k: int):
+        """bsr_search_parallel: collective; (idx, dist, count) on rank 0, None elsewhere."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        nq = q.shape[0]
+        if q.shape[1] != engine.store.dim:
+            raise BsrError(_lib.BSR_ERR_INVALID, "query length differs from the store's dimension")
+        if self.rank == 0:
+            idx = np.zeros((nq, top_k), dtype=np.uint64)
+            dist = np.zeros((nq, top_k), dtype=np.float32)
+            count = np.zeros(nq, dtype=np.uint32)
+            args = (idx.ctypes.data, dist.ctypes.data, count.ctypes.data)
+        else:
+            idx = dist = count = None
+            args = (None, None, None)
+        _lib.check(_lib.lib().bsr_search_parallel(engine.store.handle, self._h, q.ctypes.data, nq, top_k, *args))
+        return (idx, dist, count) if self.rank == 0 else None
+
+    def close(self) -> None:
+        if self._h:
+            _lib.lib().bsr_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+
 # ---------------------------------------------------------------------------------------------
 # resident shards: the reference re-reads global.parquet inside every compute_local_top_k call
 # (metrics.rs:23); here a (dir, rank, size) block is decoded once and stays in HBM.
@@ -343,6 +387,11 @@ def parallel_top_k_similarity_search(world, rank: int, size: int, vstore_dir, to
     `slots` candidates per rank (NCCL over NVLink) -> on-device merge on root -> unpack."""
     if verbose:
         print(f"[Rank {rank}] Calculating top-{top_k} distances")
+    if isinstance(world, BsrComm):
+        # the library's own communicator: scan, ncclAllGather, merge and unpack in one C-ABI call
+        eng = engine or open_shard(vstore_dir, rank, size, device=device)
+        res = world.search(eng, np.asarray(target_vector, dtype=np.float32), top_k)
+        return _pairs(res[0][0], res[1][0], res[2][0]) if res is not None else None
     slots = candidate_slots(top_k)
     target = np.asarray(target_vector, dtype=np.float32).reshape(1, -1)
     try:

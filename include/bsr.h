@@ -159,6 +159,30 @@ BSR_API int bsr_unpack_device(bsr_store *store, const uint64_t *d_candidates, ui
 BSR_API int bsr_merge_host(bsr_store *store, const uint64_t *idx, const float *dist, uint64_t n,
                            uint32_t top_k, uint64_t *out_idx, float *out_dist, uint32_t *out_count);
 
+/* ---- multi-rank search inside the library (for hosts without their own GPU communicator) ------
+ * One rank = one process = one GPU = one bsr_store shard, as in the reference (one MPI process per
+ * rank).  The candidate exchange (gather_top_k_results, metrics.rs:56-138) is an ncclAllGather of
+ * the per-shard candidate slots over NVLink; NCCL is resolved at run time (dlopen of libnccl.so.2,
+ * reusing the copy already loaded in the process if there is one). */
+#define BSR_COMM_ID_BYTES 128
+typedef struct bsr_comm bsr_comm;
+
+/* Rank 0 creates the id and hands it to every rank over the host's own channel (in the reference's
+ * world: one MPI_Bcast, like the query at src/main.rs:123-125). */
+BSR_API int bsr_comm_unique_id(uint8_t id[BSR_COMM_ID_BYTES]);
+/* Collective: every rank calls it with the same id and n_ranks; `device` is the rank's GPU. */
+BSR_API int bsr_comm_create(const uint8_t id[BSR_COMM_ID_BYTES], int n_ranks, int rank, int device,
+                            bsr_comm **out);
+BSR_API int bsr_comm_destroy(bsr_comm *comm);
+
+/* parallel_top_k_similarity_search (metrics.rs:174-206).  Collective: every rank passes its shard
+ * and the same queries (host memory).  Scan of the local shard -> all-gather of the candidate slots
+ * -> on root: on-device merge, unpack, copy to the host outputs (as bsr_search).  On the other
+ * ranks the outputs are not written (the reference returns None there); they may be NULL. */
+BSR_API int bsr_search_parallel(bsr_store *shard, bsr_comm *comm, const float *queries,
+                                uint32_t n_queries, uint32_t top_k, uint64_t *out_idx,
+                                float *out_dist, uint32_t *out_count);
+
 /* BF16 stores only: query batches of at least `min_batch` queries (default 32) are scanned on the
  * tensor cores (tcgen05, queries in tensor memory).  That path is not bit-exact: the tensor core
  * accumulates the (exact) bf16 products in a different order, so distances agree with the exact

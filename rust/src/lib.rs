@@ -15,6 +15,12 @@ pub mod ffi {
         _private: [u8; 0],
     }
 
+    #[repr(C)]
+    pub struct bsr_comm {
+        _private: [u8; 0],
+    }
+
+    pub const BSR_COMM_ID_BYTES: usize = 128;
     pub const BSR_OK: c_int = 0;
     pub const BSR_F32: c_int = 0;
     pub const BSR_BF16: c_int = 1;
@@ -56,6 +62,13 @@ pub mod ffi {
         pub fn bsr_merge_host(store: *mut bsr_store, idx: *const u64, dist: *const f32, n: u64,
                               top_k: u32, out_idx: *mut u64, out_dist: *mut f32,
                               out_count: *mut u32) -> c_int;
+        pub fn bsr_comm_unique_id(id: *mut u8) -> c_int;
+        pub fn bsr_comm_create(id: *const u8, n_ranks: c_int, rank: c_int, device: c_int,
+                               out: *mut *mut bsr_comm) -> c_int;
+        pub fn bsr_comm_destroy(comm: *mut bsr_comm) -> c_int;
+        pub fn bsr_search_parallel(shard: *mut bsr_store, comm: *mut bsr_comm, queries: *const f32,
+                                   n_queries: u32, top_k: u32, out_idx: *mut u64, out_dist: *mut f32,
+                                   out_count: *mut u32) -> c_int;
         pub fn bsr_store_set_tensor_min_batch(store: *mut bsr_store, min_batch: u32) -> c_int;
         pub fn bsr_store_launch_count(store: *const bsr_store, n_launches: *mut u64) -> c_int;
         pub fn bsr_store_last_scan_ms(store: *mut bsr_store, ms: *mut f32) -> c_int;
@@ -220,6 +233,54 @@ pub fn compute_global_top_k(scratch: &mut GpuVectorstore, global_indices: Vec<us
                             top_k as u32, idx.as_mut_ptr(), dist.as_mut_ptr(), &mut count)
     })?;
     Ok((0..count as usize).map(|i| (idx[i] as usize, dist[i])).collect())
+}
+
+/// The library's own NCCL communicator (one per rank = per process = per GPU).
+pub struct DeviceWorld {
+    handle: *mut ffi::bsr_comm,
+    pub rank: i32,
+    pub size: i32,
+}
+
+impl DeviceWorld {
+    /// Rank 0 creates the id; broadcast the 128 bytes with the host's own channel
+    /// (`world.process_at_rank(ROOT).broadcast_into(&mut id)` in the reference's rsmpi world).
+    pub fn unique_id() -> Result<[u8; ffi::BSR_COMM_ID_BYTES], BsrError> {
+        let mut id = [0u8; ffi::BSR_COMM_ID_BYTES];
+        check(unsafe { ffi::bsr_comm_unique_id(id.as_mut_ptr()) })?;
+        Ok(id)
+    }
+    pub fn new(id: &[u8; ffi::BSR_COMM_ID_BYTES], size: i32, rank: i32, device: i32) -> Result<Self, BsrError> {
+        let mut handle = std::ptr::null_mut();
+        check(unsafe { ffi::bsr_comm_create(id.as_ptr(), size, rank, device, &mut handle) })?;
+        Ok(Self { handle, rank, size })
+    }
+}
+
+impl Drop for DeviceWorld {
+    fn drop(&mut self) {
+        unsafe { ffi::bsr_comm_destroy(self.handle) };
+    }
+}
+
+/// `parallel_top_k_similarity_search` (src/mpi_helpers/metrics.rs:174-206): `Some` on root.
+pub fn parallel_top_k_similarity_search(world: &DeviceWorld, shard: &mut GpuVectorstore, top_k: usize,
+                                        target_vector: &Vec<f32>)
+    -> Result<Option<Vec<(usize, f32)>>, BsrError> {
+    let root = world.rank == 0;
+    let mut idx = vec![0u64; top_k];
+    let mut dist = vec![0f32; top_k];
+    let mut count = 0u32;
+    check(unsafe {
+        ffi::bsr_search_parallel(shard.handle, world.handle, target_vector.as_ptr(), 1, top_k as u32,
+                                 if root { idx.as_mut_ptr() } else { std::ptr::null_mut() },
+                                 if root { dist.as_mut_ptr() } else { std::ptr::null_mut() },
+                                 if root { &mut count } else { std::ptr::null_mut() })
+    })?;
+    if !root {
+        return Ok(None);
+    }
+    Ok(Some((0..count as usize).map(|i| (idx[i] as usize, dist[i])).collect()))
 }
 
 impl Drop for GpuVectorstore {

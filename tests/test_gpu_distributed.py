@@ -41,6 +41,13 @@ def _worker(rank, size, port, n_rows, k, q_out):
         out = []
         for query in (q.cpu().numpy(), np.linspace(-1, 1, 768, dtype=np.float32)):
             out.append(bsr.parallel_top_k_similarity_search(None, rank, size, None, k, query, engine=eng))
+        # the same search through the library's own communicator (bsr_comm_*, bsr_search_parallel)
+        ids = [bsr.BsrComm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        comm = bsr.BsrComm(ids[0], size, rank, rank)
+        for query in (q.cpu().numpy(), np.linspace(-1, 1, 768, dtype=np.float32)):
+            out.append(bsr.parallel_top_k_similarity_search(comm, rank, size, None, k, query, engine=eng))
+        comm.close()
         q_out.put((rank, out))
         dist.barrier()
     finally:
@@ -67,7 +74,7 @@ def test_nccl_parallel_search(k):
         p.join(timeout=120)
         assert p.exitcode == 0
     rows = co.generate_rows(0x5EED0001, 0, n_rows, 768)
-    for qi, query in enumerate((rows[0], np.linspace(-1, 1, 768, dtype=np.float32))):
+    for qi, query in enumerate((rows[0], np.linspace(-1, 1, 768, dtype=np.float32)) * 2):
         wi, wd = co.parallel_top_k_similarity_search(rows, size, k, query, n_threads=8)
         got = res[0][qi]
         assert [p[0] for p in got] == wi.tolist()
