@@ -94,3 +94,23 @@ def test_store_paths():
     import inspect
     assert 'f"rank_{rank}.parquet"' in inspect.getsource(bsr.get_local_vstore)
     assert '"global.parquet"' in inspect.getsource(bsr.get_global_vstore)
+
+
+def test_timing_report_format():
+    """BenchmarkManager::generate_report text (src/mpi_helpers/benchmark.rs:313-416)."""
+    from better_search_rag_rust_b200.benchmark import BenchmarkManager, BenchmarkTiming, BenchmarkTimer
+    m = BenchmarkManager(0)
+    m.record(BenchmarkTiming("similarity_search", 0.00123, None))
+    m.record(BenchmarkTiming("metrics_calculation", 2.5, 7))
+    t = BenchmarkTimer.start("total_execution").stop()
+    assert t.name == "total_execution" and t.seconds() >= 0.0
+    rep = m.generate_report(None, {"similarity_search": 1.23})
+    assert rep.splitlines() == [
+        "==== PARALLEL PERFORMANCE REPORT ====", "",
+        "Operation: metrics_calculation",
+        "  Min time: 2.5000 sec (Rank 0)", "  Max time: 2.5000 sec (Rank 0)", "  Avg time: 2.5000 sec",
+        "Operation: similarity_search",
+        "  Min time: 0.0012 sec (Rank 0)", "  Max time: 0.0012 sec (Rank 0)", "  Avg time: 0.0012 sec",
+        "  Speedup: 1000.00x"]
+    assert BenchmarkManager(1).generate_report(None) == ""
+    assert m.get("metrics_calculation").throughput() == pytest.approx(2.8)
