@@ -594,65 +594,91 @@ static unsigned scan_grid(const bsr_store* s, u32 n_panels, int warps_per_cta) {
 }
 
 // ---- tcgen05 path (BF16 stores, large batches) -------------------------------------------------
-static u32 tensor_stage_kb() {
-    u32 v = kTcStageKB;
+// Ring shape (measured on B200, 10 M x 768 bf16, top-100): every stage costs a fixed wait/arm/copy +
+// wait/issue/commit handshake, so stages are large.  Single CTA: 3 x 48 KiB.  Cluster of 2: one
+// whole tile (96 KiB) per stage, 2 stages.  BSR_TENSOR_STAGE_KB / BSR_TENSOR_STAGES override.
+static u32 tensor_stage_kb(u32 cluster) {
+    u32 v = cluster > 1 ? kTcStageKB : kTcStageKB / 2;
     if (const char* e = getenv("BSR_TENSOR_STAGE_KB")) v = (u32)std::min<int>(kTcStageKB, std::max(1, atoi(e)));
     return v;
 }
-static size_t tensor_smem_bytes(u32 K, u32 stages) {
-    (void)K;
-    return (size_t)stages * tensor_stage_kb() * kTileBytes + (size_t)kTcNormSlots * 2 * kTcN * sizeof(float) +
+static size_t tensor_smem_bytes(u32 stage_kb, u32 stages) {
+    return (size_t)stages * stage_kb * kTileBytes + (size_t)kTcNormSlots * 2 * kTcN * sizeof(float) +
            (size_t)(2 * stages + 5 + 2 * kTcNormSlots) * sizeof(u64) + 16 + 1024;  // + ring alignment slack
 }
-static u32 tensor_stages(const bsr_store* s, u32 K) {
-    // 48 KiB stages; even one holds the end-of-kernel sort scratch (4 warps x 8 KiB)
-    u32 st = 3;
+static u32 tensor_stages(const bsr_store* s, u32 cluster) {
+    // even one stage holds the 32 KiB nothing else needs; >= 2 to overlap copy and MMA
+    u32 st = cluster > 1 ? 2 : 3;
     if (const char* e = getenv("BSR_TENSOR_STAGES")) st = std::max(2, atoi(e));
-    while (st >= 2 && tensor_smem_bytes(K, st) + 2048 > s->smem_optin) st--;
+    while (st >= 2 && tensor_smem_bytes(tensor_stage_kb(cluster), st) + 2048 > s->smem_optin) st--;
     return st;
 }
 static bool tensor_eligible(const bsr_store* s, u32 nq, u32 K) {
     return is_bf16(s) && s->tensor_min_batch > 0 && nq >= s->tensor_min_batch && s->kb <= kTcMaxKB &&
-           K <= 128 && tensor_stages(s, K) >= 2;
+           K <= 128 && tensor_stages(s, 1) >= 2 && tensor_stages(s, 2) >= 2;
+}
+
+template <int C>
+static int launch_tensor(bsr_store* s, const TensorScanArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
+    static thread_local bool configured[64] = {false};
+    if (!configured[s->device & 63]) {
+        cudaFuncAttributes fa;
+        CU(cudaFuncGetAttributes(&fa, scan_topk_bf16_tensor_kernel<C>));
+        CU(cudaFuncSetAttribute(scan_topk_bf16_tensor_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(s->smem_optin - fa.sharedSizeBytes)));
+        configured[s->device & 63] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&cfg, scan_topk_bf16_tensor_kernel<C>, a));
+    s->launches++;
+    return BSR_OK;
 }
 
 static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u64* d_cand, u64* d_idx,
                          float* d_dist, u32* d_count, cudaStream_t st) {
     const u32 K = bsr_candidate_slots(k);
     const u32 n_tiles = (u32)((s->n_rows + kTcN - 1) / kTcN);
-    const unsigned grid = std::max(1u, std::min<unsigned>((unsigned)s->n_sm, n_tiles));
-    const u32 stages = tensor_stages(s, K);
-    const size_t smem = tensor_smem_bytes(K, stages);
-    static thread_local bool configured[64] = {false};
-    if (!configured[s->device & 63]) {
-        cudaFuncAttributes fa;
-        CU(cudaFuncGetAttributes(&fa, scan_topk_bf16_tensor_kernel));
-        CU(cudaFuncSetAttribute(scan_topk_bf16_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(s->smem_optin - fa.sharedSizeBytes)));
-        configured[s->device & 63] = true;
-    }
-    TRY(ensure(s->cta_keys, (size_t)nq * grid * K * sizeof(u64)));
-    const size_t gm_bytes = (size_t)kTcQ * ((k + kTcN - 1) / kTcN) * kTcN * sizeof(u32);
+    // more than one 128-query group: clusters of 2 CTAs share every store tile (TMA multicast)
+    u32 C = (nq > kTcQ && s->n_sm >= 2) ? 2u : 1u;
+    if (const char* e = getenv("BSR_TENSOR_CLUSTER")) C = atoi(e) == 2 ? 2u : 1u;
+    const unsigned n_clusters = std::max(1u, std::min<unsigned>((unsigned)s->n_sm / C, n_tiles));
+    const unsigned grid = n_clusters * C;
+    const u32 QS = C * kTcQ;  // queries per launch
+    const u32 stages = tensor_stages(s, C), stage_kb = tensor_stage_kb(C);
+    const size_t smem = tensor_smem_bytes(stage_kb, stages);
+    TRY(ensure(s->cta_keys, (size_t)nq * n_clusters * K * sizeof(u64)));
+    const size_t gm_bytes = (size_t)QS * ((k + kTcN - 1) / kTcN) * kTcN * sizeof(u32);
     TRY(ensure(s->d_gtau, gm_bytes));
-    TRY(ensure(s->d_surv, (size_t)kTcQ * grid * 2 * kTcSurvivorCap * sizeof(u64) + (size_t)kTcQ * grid * sizeof(u32) +
-                              kTcQ * sizeof(float)));
+    const size_t surv_bytes = (size_t)QS * n_clusters * 2 * kTcSurvivorCap * sizeof(u64);
+    TRY(ensure(s->d_surv, surv_bytes + (size_t)QS * n_clusters * sizeof(u32) + QS * sizeof(float)));
     const u32 max_per_cta = std::max<u32>(2, kMergeMaxKeys / K);
-    const size_t inter = (size_t)nq * ((grid + max_per_cta - 1) / max_per_cta) * K * sizeof(u64);
+    const size_t inter = (size_t)nq * ((n_clusters + max_per_cta - 1) / max_per_cta) * K * sizeof(u64);
     TRY(ensure(s->merge_a, inter));
     TRY(ensure(s->merge_b, inter));
     CU(cudaEventRecord(s->ev_scan0, st));
-    for (u32 q0 = 0; q0 < nq; q0 += kTcQ) {
+    for (u32 q0 = 0; q0 < nq; q0 += QS) {
         TensorScanArgs a;
         a.tiles = (const unsigned char*)s->panels;
         a.norms = s->norms;
         a.inv_norms = s->inv_norms;
         a.queries = d_queries + (size_t)q0 * s->dim;
-        a.cta_keys = (u64*)s->cta_keys.p + (size_t)q0 * grid * K;
+        a.cta_keys = (u64*)s->cta_keys.p + (size_t)q0 * n_clusters * K;
         a.g_gm = (u32*)s->d_gtau.p;
         a.survivors = (u64*)s->d_surv.p;
-        a.surv_count = (u32*)((char*)s->d_surv.p + (size_t)kTcQ * grid * 2 * kTcSurvivorCap * sizeof(u64));
-        a.q_mag = (float*)(a.surv_count + (size_t)kTcQ * grid);
-        a.nq_valid = std::min(kTcQ, nq - q0);
+        a.surv_count = (u32*)((char*)s->d_surv.p + surv_bytes);
+        a.q_mag = (float*)(a.surv_count + (size_t)QS * n_clusters);
+        a.nq_valid = std::min(QS, nq - q0);
         a.n_rows = (u32)s->n_rows;
         a.n_tiles = n_tiles;
         a.KB = s->kb;
@@ -661,15 +687,15 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
         a.k_pad = K;
         a.row_base = (u32)s->row_base;
         a.stages = stages;
-        a.stage_kb = tensor_stage_kb();
+        a.stage_kb = stage_kb;
         CU(cudaMemsetAsync(s->d_gtau.p, 0, gm_bytes, st));  // 0 < ordered(-inf): "nobody published yet"
         TRY(prof_begin(s, st));
-        scan_topk_bf16_tensor_kernel<<<grid, kTcThreads, smem, st>>>(a);
-        s->launches++;
-        CU(cudaGetLastError());
+        if (C == 2) TRY(launch_tensor<2>(s, a, grid, smem, st));
+        else TRY(launch_tensor<1>(s, a, grid, smem, st));
         {
-            const u32 lists = a.nq_valid * grid, wpb = 4;  // 4 warps x 8 KiB of sort scratch per CTA
-            finalize_survivors_kernel<<<(lists + wpb - 1) / wpb, wpb * 32, wpb * kTcSurvivorCap * sizeof(u64), st>>>(a, grid);
+            const u32 lists = a.nq_valid * n_clusters, wpb = 4;  // 4 warps x 8 KiB of sort scratch per CTA
+            finalize_survivors_kernel<<<(lists + wpb - 1) / wpb, wpb * 32, wpb * kTcSurvivorCap * sizeof(u64), st>>>(
+                a, n_clusters);
             s->launches++;
             CU(cudaGetLastError());
         }
@@ -677,7 +703,7 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
     }
     CU(cudaEventRecord(s->ev_scan1, st));
     s->scan_timed = true;
-    TRY(merge_tree(s, (const u64*)s->cta_keys.p, grid, nq, K, K, (size_t)grid * K, d_cand, st));
+    TRY(merge_tree(s, (const u64*)s->cta_keys.p, n_clusters, nq, K, K, (size_t)n_clusters * K, d_cand, st));
     if (d_idx) {
         unpack_kernel<<<nq, 128, 0, st>>>(d_cand, K, k, d_idx, d_dist, d_count);
         s->launches++;

@@ -29,6 +29,15 @@
 //       again at the end, when the bound is mature.
 //     - at the end each warp bitonic-sorts its queries' survivors and writes the best k_pad.
 //
+// * clusters: with more than 128 queries in a launch, CTAs run as clusters of C = 2; the CTAs of a
+//   cluster hold different 128-query groups in their TMEM and walk the SAME store tiles.  Every ring
+//   stage is fetched from HBM once: CTA r copies the r-th 1/C of the stage with
+//   cp.async.bulk ... .multicast::cluster into the shared memory of all C CTAs (each CTA's full
+//   barrier counts the whole stage).  A slot is refilled only when every CTA of the cluster has
+//   released it: each MMA thread's tcgen05.commit is multicast to the slot's empty barrier in all C
+//   CTAs (barrier count C).  This halves the HBM bytes per query and moves the kernel from
+//   HBM-bound towards tensor-bound.
+//
 // Numerics: products of bf16 values are exact in binary32; the tensor core's accumulation order
 // differs from the reference's left-to-right fold, so distances agree with the oracle (run on the
 // bf16-rounded rows and queries) to ~1e-6, not bit for bit -- the documented "looser bound" of
@@ -57,12 +66,12 @@ struct TensorScanArgs {
     const float* norms;          // |a| per row
     const float* inv_norms;      // 1/|a| per row (0 where |a| is 0, inf or NaN)
     const float* queries;        // [nq_valid][dim] binary32, device
-    u64* cta_keys;               // [nq_valid][gridDim.x][k_pad]
-    u32* g_gm;                   // [64*T][128] global class maxima (ordered-float bits), 0 before the launch
-    u64* survivors;              // [128][gridDim.x][2 * kTcSurvivorCap] raw (row, score) pairs
-    u32* surv_count;             // [128][gridDim.x] survivors per (query, CTA)
-    float* q_mag;                // [128] |b| of the bf16-rounded queries (written by CTA 0)
-    u32 nq_valid;                // <= 128
+    u64* cta_keys;               // [nq_valid][n_clusters][k_pad]
+    u32* g_gm;                   // [64*T][128*C] global class maxima (ordered-float bits), 0 before the launch
+    u64* survivors;              // [128*C][n_clusters][2 * kTcSurvivorCap] raw (row, score) pairs
+    u32* surv_count;             // [128*C][n_clusters] survivors per (query, cluster)
+    float* q_mag;                // [128*C] |b| of the bf16-rounded queries (written by cluster 0)
+    u32 nq_valid;                // <= 128 * cluster size
     u32 n_rows, n_tiles, KB, dim, k, k_pad, row_base, stages;
     u32 stage_kb;                // 64-column blocks per ring stage (<= kTcStageKB)
 };
@@ -72,6 +81,54 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(u32 bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// ---- cluster helpers ----
+__device__ __forceinline__ u32 cluster_ctarank() {
+    u32 r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(u32 local_bar, u32 rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(local_bar), "r"(rank)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(u32 bar, u32 parity) {
+    u32 ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// global -> shared bulk copy delivered to the same offset in every CTA of `mask`; each destination
+// CTA's barrier (same offset) receives the complete_tx
+__device__ __forceinline__ void bulk_g2s_multicast(u32 dst, const void* src, u32 bytes, u32 bar, unsigned short mask,
+                                                   u64 policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint "
+        "[%0], [%1], %2, [%3], %4, %5;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "h"(mask), "l"(policy)
+        : "memory");
+}
+
+// the same completion signalled to the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_multicast(u32 bar, unsigned short mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"(mask)
+        : "memory");
 }
 __device__ __forceinline__ void tc_commit(u32 bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
@@ -180,6 +237,7 @@ __device__ __noinline__ u64 compact_survivors(const TensorScanArgs& a, u64* buf,
     return keys_tmp[k - 1];
 }
 
+template <int C>  // C = cluster size: CTAs of a cluster share the store tiles (TMA multicast)
 __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(const TensorScanArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const u32 S = a.stages, KB = a.KB, SKB = a.stage_kb;
@@ -203,7 +261,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
     if (tid == 0) {
         for (u32 i = 0; i < S; i++) {
             mbar_init(smem_u32(full_bar + i), 1);
-            mbar_init(smem_u32(empty_bar + i), 1);
+            mbar_init(smem_u32(empty_bar + i), C);  // one tcgen05.commit from every CTA of the cluster
         }
         for (u32 i = 0; i < 2; i++) {
             mbar_init(smem_u32(accf_bar + i), 1);
@@ -223,14 +281,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    if (C > 1) cluster_sync_all();  // barrier inits visible to the peers before any remote arrive
+    else __syncthreads();
     tc_fence_after();
     const u32 tmem = *s_tmem;
     const u32 tmem_a = tmem + kTcAccCols;  // A operand starts after the accumulators
 
     // tile sequence of this CTA: its tiles in order, the first `learn` of them bound-only, then those
     // same tiles once more at the end
-    const u32 my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const u32 crank = C > 1 ? cluster_ctarank() : 0;
+    const u32 cluster_id = blockIdx.x / C, n_clusters = gridDim.x / C;
+    const u32 my_tiles = cluster_id < a.n_tiles ? (a.n_tiles - 1 - cluster_id) / n_clusters + 1 : 0;
     const u32 learn = min(kTcLearnTiles, my_tiles);
     const u32 n_seq = my_tiles + learn;
 
@@ -241,7 +302,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
             u32 slot = 0, phase = 0;
             for (u32 sq = 0; sq < n_seq; sq++) {
                 const u32 li = sq < my_tiles ? sq : sq - my_tiles;
-                const size_t tile = (size_t)blockIdx.x + (size_t)li * gridDim.x;
+                const size_t tile = (size_t)cluster_id + (size_t)li * n_clusters;
                 {   // the tile's 64 norms and inverse norms (2 x 256 bytes)
                     const u32 ns = sq % kTcNormSlots;
                     mbar_wait(smem_u32(nempty_bar + ns), ((sq / kTcNormSlots) & 1) ^ 1);
@@ -254,10 +315,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
                 }
                 for (u32 kb0 = 0; kb0 < KB; kb0 += SKB) {  // one copy per stage (several column blocks)
                     const u32 bytes = min(SKB, KB - kb0) * kTileBytes;
-                    mbar_wait(smem_u32(empty_bar + slot), phase ^ 1);
-                    mbar_expect_tx(smem_u32(full_bar + slot), bytes);
-                    bulk_g2s(smem_u32(ring + (size_t)slot * stage_bytes), a.tiles + (tile * KB + kb0) * kTileBytes,
-                             bytes, smem_u32(full_bar + slot), policy);
+                    // every CTA of the cluster has retired its MMAs on this slot
+                    if (C > 1) mbar_wait_cluster(smem_u32(empty_bar + slot), phase ^ 1);
+                    else mbar_wait(smem_u32(empty_bar + slot), phase ^ 1);
+                    const unsigned char* src = a.tiles + (tile * KB + kb0) * kTileBytes;
+                    const u32 dst = smem_u32(ring + (size_t)slot * stage_bytes);
+                    if (C > 1) {
+                        // multicast my 1/C of the stage to all CTAs of the cluster
+                        mbar_expect_tx(smem_u32(full_bar + slot), bytes);
+                        const u32 part = bytes / C;
+                        bulk_g2s_multicast(dst + crank * part, src + (size_t)crank * part, part,
+                                           smem_u32(full_bar + slot), (unsigned short)((1u << C) - 1), policy);
+                    } else {
+                        mbar_expect_tx(smem_u32(full_bar + slot), bytes);
+                        bulk_g2s(dst, src, bytes, smem_u32(full_bar + slot), policy);
+                    }
                     if (++slot == S) {
                         slot = 0;
                         phase ^= 1;
@@ -288,7 +360,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
                             tc_mma_ts(d_tmem, tmem_a + (kb * 4 + k4) * 8, desc + (u64)(k4 * 2), kIdescBf16M128N64,
                                       (kb | k4) != 0 ? 1u : 0u);
                     }
-                    tc_commit(smem_u32(empty_bar + slot));  // slot reusable once these MMAs retire
+                    // slot reusable once these MMAs retire -- in every CTA that shares the stage
+                    if (C > 1) tc_commit_multicast(smem_u32(empty_bar + slot), (unsigned short)((1u << C) - 1));
+                    else tc_commit(smem_u32(empty_bar + slot));
                     if (++slot == S) {
                         slot = 0;
                         phase ^= 1;
@@ -299,7 +373,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
         }
     } else {
         // ================= warps 0-3: query -> TMEM, then epilogue =================
-        const u32 q = tid;  // TMEM lane == query index within the CTA
+        const u32 q = crank * kTcQ + tid;  // query index within the launch; TMEM lane == tid
+        const u32 QS = C * kTcQ;           // queries per launch (stride of the per-query arrays)
         const bool active = q < a.nq_valid;
         const float* qp = a.queries + (size_t)(active ? q : 0) * a.dim;
         const u32 lane_addr = ((u32)(warp * 32) << 16);
@@ -343,14 +418,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
 
         // classes: (row position in its tile) x (CTA group); this CTA owns 64 of the kc classes
         const u32 T = (a.k + kTcN - 1) / kTcN, kc = T * kTcN;
-        const u32 group = blockIdx.x % T;
-        u32* g_gm = a.g_gm + q;  // class c of my query: g_gm[c * 128]  (a warp touches 128 contiguous bytes)
+        const u32 group = cluster_id % T;
+        u32* g_gm = a.g_gm + q;  // class c of my query: g_gm[c * QS]  (a warp touches 128 contiguous bytes)
         float gmr[kTcN];  // my 64 class maxima, in registers
 #pragma unroll
         for (u32 j = 0; j < kTcN; j++) gmr[j] = -INFINITY;
 
         // survivor slots of this (CTA, query): the upper half doubles as scratch for a compaction
-        u64* surv_buf = a.survivors + ((size_t)q * gridDim.x + blockIdx.x) * (2 * kTcSurvivorCap);
+        u64* surv_buf = a.survivors + ((size_t)q * n_clusters + cluster_id) * (2 * kTcSurvivorCap);
         u32 surv_cnt = 0;
         float thr = -INFINITY;    // prune rows with t < thr, t = S / |a|
 
@@ -358,7 +433,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
             const u32 buf = sq & 1;
             const u32 li = sq < my_tiles ? sq : sq - my_tiles;
             const bool learn_only = sq < learn;
-            const u32 tile = blockIdx.x + li * gridDim.x;
+            const u32 tile = cluster_id + li * n_clusters;
             const u32 row0 = tile * kTcN;
             const u32 ns = sq % kTcNormSlots;
             const float* na_s = s_norm + (size_t)ns * 2 * kTcN;
@@ -449,7 +524,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
                     for (u32 c0 = 0; c0 < kc; c0 += kTcN) {  // one 64-class group at a time
                         u32 their_bits[kTcN];
 #pragma unroll
-                        for (u32 i = 0; i < kTcN; i++) their_bits[i] = __ldcg(g_gm + (size_t)(c0 + i) * kTcQ);  // independent, coalesced L2 reads
+                        for (u32 i = 0; i < kTcN; i++) their_bits[i] = __ldcg(g_gm + (size_t)(c0 + i) * QS);  // independent, coalesced L2 reads
                         const bool mine_group = (c0 == group * kTcN);
 #pragma unroll
                         for (u32 i = 0; i < kTcN; i++) {
@@ -457,7 +532,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
                             float best = their_bits[i] ? f32_from_ordered(their_bits[i]) : -INFINITY;
                             if (mine_group) {
                                 if (gmr[i] > best) {
-                                    atomicMax(g_gm + (size_t)(c0 + i) * kTcQ, f32_ordered(gmr[i]));
+                                    atomicMax(g_gm + (size_t)(c0 + i) * QS, f32_ordered(gmr[i]));
                                     best = gmr[i];
                                 } else {
                                     gmr[i] = best;
@@ -473,13 +548,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
         }
         // exact keys + sort of the survivors happen in finalize_survivors_kernel (fully parallel)
         if (active) {
-            a.surv_count[(size_t)q * gridDim.x + blockIdx.x] = surv_cnt;
-            if (blockIdx.x == 0) a.q_mag[q] = mag_b;
+            a.surv_count[(size_t)q * n_clusters + cluster_id] = surv_cnt;
+            if (cluster_id == 0) a.q_mag[q] = mag_b;
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (C > 1) cluster_sync_all();  // no CTA may leave while a peer can still write into its shared memory
+    else __syncthreads();
     if (warp == 5) {
         __syncwarp();
         tc_fence_after();
