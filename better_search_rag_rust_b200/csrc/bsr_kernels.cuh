@@ -366,7 +366,18 @@ __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta
     for (int q = 0; q < NQ; q++) {
         u64 v = kKeyMax;
         const u64* src = cta_keys + q * q_stride;
-        for (u32 l = warp; l < gridDim.x; l += W) v = warp_merge32(v, ldcg_u64(src + (size_t)l * 32 + lane), lane);
+        // this warp's lists are l = warp, warp+W, ...: fetch eight at a time (independent L2 reads,
+        // one round trip) and only then run the dependent merges
+        for (u32 l0 = warp; l0 < gridDim.x; l0 += 8 * W) {
+            u64 t[8];
+#pragma unroll
+            for (u32 i = 0; i < 8; i++) {
+                const u32 l = l0 + i * W;
+                t[i] = l < gridDim.x ? ldcg_u64(src + (size_t)l * 32 + lane) : kKeyMax;
+            }
+#pragma unroll
+            for (u32 i = 0; i < 8; i++) v = warp_merge32(v, t[i], lane);
+        }
         lists[((size_t)q * W + warp) * 32 + lane] = v;
     }
     __syncthreads();
