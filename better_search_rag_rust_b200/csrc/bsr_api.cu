@@ -597,34 +597,34 @@ static unsigned scan_grid(const bsr_store* s, u32 n_panels, int warps_per_cta) {
 // Ring shape (measured on B200, 10 M x 768 bf16, top-100): every stage costs a fixed wait/arm/copy +
 // wait/issue/commit handshake, so stages are large.  Single CTA: 3 x 48 KiB.  Cluster of 2: one
 // whole tile (96 KiB) per stage, 2 stages.  BSR_TENSOR_STAGE_KB / BSR_TENSOR_STAGES override.
-static u32 tensor_stage_kb(u32 cluster) {
-    u32 v = cluster > 1 ? kTcStageKB : kTcStageKB / 2;
+static u32 tensor_stage_kb(u32 mode) {
+    u32 v = mode == 0 ? kTcStageKB / 2 : kTcStageKB;  // pair mode: 12 half-height blocks = 48 KiB
     if (const char* e = getenv("BSR_TENSOR_STAGE_KB")) v = (u32)std::min<int>(kTcStageKB, std::max(1, atoi(e)));
     return v;
 }
-static size_t tensor_smem_bytes(u32 stage_kb, u32 stages) {
-    return (size_t)stages * stage_kb * kTileBytes + (size_t)kTcNormSlots * 2 * kTcN * sizeof(float) +
-           (size_t)(2 * stages + 5 + 2 * kTcNormSlots) * sizeof(u64) + 16 + 1024;  // + ring alignment slack
+static size_t tensor_smem_bytes(u32 stage_kb, u32 stages, u32 mode = 0) {
+    const size_t blk = mode == 2 ? kTileBytes / 2 : kTileBytes;
+    return (size_t)stages * stage_kb * blk + (size_t)kTcNormSlots * 2 * kTcN * sizeof(float) +
+           (size_t)(3 * stages + 5 + 2 * kTcNormSlots) * sizeof(u64) + 16 + 1024;  // + ring alignment slack
 }
-static u32 tensor_stages(const bsr_store* s, u32 cluster) {
-    // even one stage holds the 32 KiB nothing else needs; >= 2 to overlap copy and MMA
-    u32 st = cluster > 1 ? 2 : 3;
+static u32 tensor_stages(const bsr_store* s, u32 mode) {
+    u32 st = mode == 1 ? 2 : 3;
     if (const char* e = getenv("BSR_TENSOR_STAGES")) st = std::max(2, atoi(e));
-    while (st >= 2 && tensor_smem_bytes(tensor_stage_kb(cluster), st) + 2048 > s->smem_optin) st--;
+    while (st >= 2 && tensor_smem_bytes(tensor_stage_kb(mode), st, mode) + 2048 > s->smem_optin) st--;
     return st;
 }
 static bool tensor_eligible(const bsr_store* s, u32 nq, u32 K) {
     return is_bf16(s) && s->tensor_min_batch > 0 && nq >= s->tensor_min_batch && s->kb <= kTcMaxKB &&
-           K <= 128 && tensor_stages(s, 1) >= 2 && tensor_stages(s, 2) >= 2;
+           K <= 128 && tensor_stages(s, 0) >= 2 && tensor_stages(s, 1) >= 2 && tensor_stages(s, 2) >= 2;
 }
 
-template <int C>
+template <int MODE>
 static int launch_tensor(bsr_store* s, const TensorScanArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
     static thread_local bool configured[64] = {false};
     if (!configured[s->device & 63]) {
         cudaFuncAttributes fa;
-        CU(cudaFuncGetAttributes(&fa, scan_topk_bf16_tensor_kernel<C>));
-        CU(cudaFuncSetAttribute(scan_topk_bf16_tensor_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CU(cudaFuncGetAttributes(&fa, scan_topk_bf16_tensor_kernel<MODE>));
+        CU(cudaFuncSetAttribute(scan_topk_bf16_tensor_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(s->smem_optin - fa.sharedSizeBytes)));
         configured[s->device & 63] = true;
     }
@@ -635,12 +635,12 @@ static int launch_tensor(bsr_store* s, const TensorScanArgs& a, unsigned grid, s
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.x = MODE == 0 ? 1 : 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CU(cudaLaunchKernelEx(&cfg, scan_topk_bf16_tensor_kernel<C>, a));
+    CU(cudaLaunchKernelEx(&cfg, scan_topk_bf16_tensor_kernel<MODE>, a));
     s->launches++;
     return BSR_OK;
 }
@@ -650,13 +650,15 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
     const u32 K = bsr_candidate_slots(k);
     const u32 n_tiles = (u32)((s->n_rows + kTcN - 1) / kTcN);
     // more than one 128-query group: clusters of 2 CTAs share every store tile (TMA multicast)
-    u32 C = (nq > kTcQ && s->n_sm >= 2) ? 2u : 1u;
-    if (const char* e = getenv("BSR_TENSOR_CLUSTER")) C = atoi(e) == 2 ? 2u : 1u;
+    // mode 0: single CTAs; 1: clusters of 2 with multicast tiles; 2: CTA pairs (cta_group::2)
+    u32 mode = (nq > kTcQ && s->n_sm >= 2) ? 1u : 0u;  // measured: multicast (1) beats pairs (2) by ~6 %
+    if (const char* e = getenv("BSR_TENSOR_MODE")) mode = (u32)std::min(2, std::max(0, atoi(e)));
+    const u32 C = mode == 0 ? 1u : 2u;
     const unsigned n_clusters = std::max(1u, std::min<unsigned>((unsigned)s->n_sm / C, n_tiles));
     const unsigned grid = n_clusters * C;
     const u32 QS = C * kTcQ;  // queries per launch
-    const u32 stages = tensor_stages(s, C), stage_kb = tensor_stage_kb(C);
-    const size_t smem = tensor_smem_bytes(stage_kb, stages);
+    const u32 stages = tensor_stages(s, mode), stage_kb = tensor_stage_kb(mode);
+    const size_t smem = tensor_smem_bytes(stage_kb, stages, mode);
     TRY(ensure(s->cta_keys, (size_t)nq * n_clusters * K * sizeof(u64)));
     const size_t gm_bytes = (size_t)QS * ((k + kTcN - 1) / kTcN) * kTcN * sizeof(u32);
     TRY(ensure(s->d_gtau, gm_bytes));
@@ -690,8 +692,9 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
         a.stage_kb = stage_kb;
         CU(cudaMemsetAsync(s->d_gtau.p, 0, gm_bytes, st));  // 0 < ordered(-inf): "nobody published yet"
         TRY(prof_begin(s, st));
-        if (C == 2) TRY(launch_tensor<2>(s, a, grid, smem, st));
-        else TRY(launch_tensor<1>(s, a, grid, smem, st));
+        if (mode == 2) TRY(launch_tensor<2>(s, a, grid, smem, st));
+        else if (mode == 1) TRY(launch_tensor<1>(s, a, grid, smem, st));
+        else TRY(launch_tensor<0>(s, a, grid, smem, st));
         {
             const u32 lists = a.nq_valid * n_clusters, wpb = 4;  // 4 warps x 8 KiB of sort scratch per CTA
             finalize_survivors_kernel<<<(lists + wpb - 1) / wpb, wpb * 32, wpb * kTcSurvivorCap * sizeof(u64), st>>>(

@@ -38,6 +38,15 @@
 //   CTAs (barrier count C).  This halves the HBM bytes per query and moves the kernel from
 //   HBM-bound towards tensor-bound.
 //
+// * pairs (MODE 2, `cta_group::2`): the two CTAs of a cluster form one M = 256 MMA.  Each CTA still
+//   owns 128 queries (its TMEM lanes) but loads only HALF of every store tile (rows 0-31 or 32-63,
+//   12 x 4 KiB copies into its own shared memory): tcgen05.mma.cta_group::2 takes the first N/2
+//   rows of B from the leader's shared memory and the rest from its peer's.  The bytes an SM
+//   ingests per flop halve -- the L2->SM path is what limits the multicast variant.  CTA 1 forwards
+//   "my half has landed" to the leader with a remote mbarrier arrive; the leader issues all MMAs and
+//   its tcgen05.commit.cta_group::2 ... multicast releases ring slots and publishes accumulators in
+//   both CTAs.
+//
 // Numerics: products of bf16 values are exact in binary32; the tensor core's accumulation order
 // differs from the reference's left-to-right fold, so distances agree with the oracle (run on the
 // bf16-rounded rows and queries) to ~1e-6, not bit for bit -- the documented "looser bound" of
@@ -82,6 +91,20 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void mbar_arrive(u32 bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// One lane of a converged warp.  The tcgen05 issue loops run with all 32 lanes (uniform control
+// flow, operands in uniform registers) and predicate only the instruction itself on this: under
+// `if (lane == 0)` the compiler wraps every UTCHMMA in an R2UR + ELECT/BRA "waterfall" (~60 cycles
+// per MMA, measured), which made the issuing thread the bottleneck of the whole kernel.
+__device__ __forceinline__ bool elect_one() {
+    u32 pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- cluster helpers ----
 __device__ __forceinline__ u32 cluster_ctarank() {
     u32 r;
@@ -130,6 +153,21 @@ __device__ __forceinline__ void tc_commit_multicast(u32 bar, unsigned short mask
         "h"(mask)
         : "memory");
 }
+__device__ __forceinline__ void tc_commit_pair_multicast(u32 bar, unsigned short mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"(mask)
+        : "memory");
+}
+// M = 256 across a CTA pair: A from both CTAs' tensor memory, B halves from both shared memories
+__device__ __forceinline__ void tc_mma_ts_pair(u32 tmem_d, u32 tmem_a, u64 desc_b, u32 idesc, u32 accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void tc_commit(u32 bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                  : "memory");
@@ -151,6 +189,8 @@ __device__ __forceinline__ u64 make_sw128_desc(u32 addr) {
 }
 // kind::f16, A = B = BF16, D = F32, both K-major, M = 128, N = 64
 constexpr u32 kIdescBf16M128N64 = (1u << 4) | (1u << 7) | (1u << 10) | ((kTcN >> 3) << 17) | ((kTcQ >> 4) << 24);
+// the same for a CTA pair: M = 256 (128 queries per CTA), N = 64
+constexpr u32 kIdescBf16M256N64 = (1u << 4) | (1u << 7) | (1u << 10) | ((kTcN >> 3) << 17) | (((2 * kTcQ) >> 4) << 24);
 
 __device__ __forceinline__ void tmem_st16(u32 taddr, const u32* r) {
     asm volatile(
@@ -237,11 +277,17 @@ __device__ __noinline__ u64 compact_survivors(const TensorScanArgs& a, u64* buf,
     return keys_tmp[k - 1];
 }
 
-template <int C>  // C = cluster size: CTAs of a cluster share the store tiles (TMA multicast)
+// MODE 0: one CTA per 128 queries.  MODE 1: clusters of 2, store tiles multicast.  MODE 2: CTA pairs,
+// cta_group::2 (M = 256), each CTA loads half of every tile.
+template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(const TensorScanArgs a) {
+    constexpr int C = MODE == 0 ? 1 : 2;
+    constexpr bool PAIR = MODE == 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const u32 S = a.stages, KB = a.KB, SKB = a.stage_kb;
-    const u32 stage_bytes = SKB * kTileBytes;
+    // bytes of one 64-column block in MY shared memory: all 64 rows, or my 32 rows in pair mode
+    const u32 blk_bytes = PAIR ? kTileBytes / 2 : kTileBytes;
+    const u32 stage_bytes = SKB * blk_bytes;
     // [ring: S stages (1024-byte aligned: swizzle atoms) | norm ring: 16 x (64 |a| + 64 1/|a|) |
     //  barriers | tmem base]
     unsigned char* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -254,20 +300,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
     u64* aready_bar = bars + 2 * S + 4;   // [1]   queries are in TMEM
     u64* nfull_bar = bars + 2 * S + 5;                     // [kTcNormSlots] TMA -> epilogue (norm blocks)
     u64* nempty_bar = bars + 2 * S + 5 + kTcNormSlots;     // [kTcNormSlots] epilogue -> TMA
-    u32* s_tmem = reinterpret_cast<u32*>(bars + 2 * S + 5 + 2 * kTcNormSlots);
+    u64* peerfull_bar = bars + 2 * S + 5 + 2 * kTcNormSlots;  // [S]   pair mode, leader: the peer's half landed
+    u32* s_tmem = reinterpret_cast<u32*>(bars + 3 * S + 5 + 2 * kTcNormSlots);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) {
         for (u32 i = 0; i < S; i++) {
             mbar_init(smem_u32(full_bar + i), 1);
-            mbar_init(smem_u32(empty_bar + i), C);  // one tcgen05.commit from every CTA of the cluster
+            // multicast mode: one tcgen05.commit from every CTA of the cluster; pair mode: the leader's
+            mbar_init(smem_u32(empty_bar + i), PAIR ? 1 : C);
+            mbar_init(smem_u32(peerfull_bar + i), 1);
         }
         for (u32 i = 0; i < 2; i++) {
             mbar_init(smem_u32(accf_bar + i), 1);
-            mbar_init(smem_u32(acce_bar + i), kTcQ);
+            mbar_init(smem_u32(acce_bar + i), PAIR ? 2 * kTcQ : kTcQ);  // pair: both CTAs' epilogues, at the leader
         }
-        mbar_init(smem_u32(aready_bar), kTcQ);
+        mbar_init(smem_u32(aready_bar), PAIR ? 2 * kTcQ : kTcQ);
         for (u32 i = 0; i < kTcNormSlots; i++) {
             mbar_init(smem_u32(nfull_bar + i), 1);
             mbar_init(smem_u32(nempty_bar + i), kTcQ);
@@ -276,9 +325,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 5) {  // whole warp: allocate all 512 TMEM columns (1 CTA per SM)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem))
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {  // both CTAs of the pair issue the 2-CTA allocation, same warp, same destination
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem))
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem))
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     if (C > 1) cluster_sync_all();  // barrier inits visible to the peers before any remote arrive
@@ -320,7 +375,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
                     else mbar_wait(smem_u32(empty_bar + slot), phase ^ 1);
                     const unsigned char* src = a.tiles + (tile * KB + kb0) * kTileBytes;
                     const u32 dst = smem_u32(ring + (size_t)slot * stage_bytes);
-                    if (C > 1) {
+                    if (PAIR) {
+                        // my 32 rows of every 64-column block: 4 KiB at offset crank * 4 KiB of the block
+                        const u32 nkb = min(SKB, KB - kb0);
+                        mbar_expect_tx(smem_u32(full_bar + slot), nkb * blk_bytes);
+                        for (u32 kk = 0; kk < nkb; kk++)
+                            bulk_g2s(dst + kk * blk_bytes, src + (size_t)kk * kTileBytes + crank * blk_bytes, blk_bytes,
+                                     smem_u32(full_bar + slot), policy);
+                    } else if (C > 1) {
                         // multicast my 1/C of the stage to all CTAs of the cluster
                         mbar_expect_tx(smem_u32(full_bar + slot), bytes);
                         const u32 part = bytes / C;
@@ -338,37 +400,74 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
             }
         }
     } else if (warp == 5) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            mbar_wait(smem_u32(aready_bar), 0);
-            tc_fence_after();
+        // ================= MMA issuer (pair mode: the leader CTA issues for both) =================
+        if (lane == 0 && PAIR && crank != 0) {
+            // non-leader CTA of a pair: tell the leader whenever my half of a stage has landed
             u32 slot = 0, phase = 0;
             for (u32 li = 0; li < n_seq; li++) {
-                const u32 buf = li & 1;
-                mbar_wait(smem_u32(acce_bar + buf), ((li >> 1) & 1) ^ 1);  // epilogue drained this accumulator
-                tc_fence_after();
-                const u32 d_tmem = tmem + buf * kTcN;
                 for (u32 kb0 = 0; kb0 < KB; kb0 += SKB) {
                     mbar_wait(smem_u32(full_bar + slot), phase);
-                    tc_fence_after();
-                    const u32 nkb = min(SKB, KB - kb0);
-                    for (u32 kk = 0; kk < nkb; kk++) {
-                        const u32 kb = kb0 + kk;
-                        const u64 desc = make_sw128_desc(smem_u32(ring + (size_t)slot * stage_bytes + (size_t)kk * kTileBytes));
-#pragma unroll
-                        for (u32 k4 = 0; k4 < 4; k4++)  // 4 x K16 per 64-column block
-                            tc_mma_ts(d_tmem, tmem_a + (kb * 4 + k4) * 8, desc + (u64)(k4 * 2), kIdescBf16M128N64,
-                                      (kb | k4) != 0 ? 1u : 0u);
-                    }
-                    // slot reusable once these MMAs retire -- in every CTA that shares the stage
-                    if (C > 1) tc_commit_multicast(smem_u32(empty_bar + slot), (unsigned short)((1u << C) - 1));
-                    else tc_commit(smem_u32(empty_bar + slot));
+                    mbar_arrive_cluster(smem_u32(peerfull_bar + slot), 0);
                     if (++slot == S) {
                         slot = 0;
                         phase ^= 1;
                     }
                 }
-                tc_commit(smem_u32(accf_bar + buf));  // accumulator complete
+            }
+        } else if (!(PAIR && crank != 0)) {
+            // the whole warp runs this loop (see elect_one); every lane polls the barriers
+            if (PAIR) mbar_wait_cluster(smem_u32(aready_bar), 0);
+            else mbar_wait(smem_u32(aready_bar), 0);
+            tc_fence_after();
+            const unsigned short both = (unsigned short)((1u << C) - 1);
+            u32 slot = 0, phase = 0;
+            for (u32 li = 0; li < n_seq; li++) {
+                const u32 buf = li & 1;
+                // the epilogue(s) drained this accumulator
+                if (PAIR) mbar_wait_cluster(smem_u32(acce_bar + buf), ((li >> 1) & 1) ^ 1);
+                else mbar_wait(smem_u32(acce_bar + buf), ((li >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const u32 d_tmem = tmem + buf * kTcN;
+                for (u32 kb0 = 0; kb0 < KB; kb0 += SKB) {
+                    mbar_wait(smem_u32(full_bar + slot), phase);
+                    if (PAIR) mbar_wait_cluster(smem_u32(peerfull_bar + slot), phase);  // ... and the peer's half
+                    tc_fence_after();
+                    const u32 nkb = min(SKB, KB - kb0);
+                    const u32 stage_addr = smem_u32(ring + (size_t)slot * stage_bytes);
+                    for (u32 kk = 0; kk < nkb; kk++) {
+                        const u32 kb = kb0 + kk;
+                        const u64 desc = make_sw128_desc(stage_addr + kk * blk_bytes);
+                        if (elect_one()) {
+#pragma unroll
+                            for (u32 k4 = 0; k4 < 4; k4++) {  // 4 x K16 per 64-column block
+                                if (PAIR)
+                                    tc_mma_ts_pair(d_tmem, tmem_a + (kb * 4 + k4) * 8, desc + (u64)(k4 * 2),
+                                                   kIdescBf16M256N64, (kb | k4) != 0 ? 1u : 0u);
+                                else
+                                    tc_mma_ts(d_tmem, tmem_a + (kb * 4 + k4) * 8, desc + (u64)(k4 * 2), kIdescBf16M128N64,
+                                              (kb | k4) != 0 ? 1u : 0u);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    // slot reusable once these MMAs retire -- in every CTA that shares the stage
+                    if (elect_one()) {
+                        if (PAIR) tc_commit_pair_multicast(smem_u32(empty_bar + slot), both);
+                        else if (C > 1) tc_commit_multicast(smem_u32(empty_bar + slot), both);
+                        else tc_commit(smem_u32(empty_bar + slot));
+                    }
+                    __syncwarp();
+                    if (++slot == S) {
+                        slot = 0;
+                        phase ^= 1;
+                    }
+                }
+                // accumulator complete (pair mode: in both CTAs' tensor memory)
+                if (elect_one()) {
+                    if (PAIR) tc_commit_pair_multicast(smem_u32(accf_bar + buf), both);
+                    else tc_commit(smem_u32(accf_bar + buf));
+                }
+                __syncwarp();
             }
         }
     } else {
@@ -409,7 +508,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
-        mbar_arrive(smem_u32(aready_bar));
+        if (PAIR && crank != 0) mbar_arrive_cluster(smem_u32(aready_bar), 0);  // the leader issues the MMAs
+        else mbar_arrive(smem_u32(aready_bar));
         const float mag_b = __fsqrt_rn(qsq);
         // The identity shortcut (src/metrics.rs:148-151) precedes every other rule.  Two vectors
         // within 1e-10 per element have sim ~ 1 unless the query itself is tiny (|b| < 1e-6): such
@@ -446,7 +546,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
             tmem_ld32(tmem + lane_addr + buf * kTcN + 32, v + 32);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
-            mbar_arrive(smem_u32(acce_bar + buf));  // scores are in registers: free the accumulator
+            // scores are in registers: free the accumulator (pair mode: at the leader, which issues)
+            if (PAIR && crank != 0) mbar_arrive_cluster(smem_u32(acce_bar + buf), 0);
+            else mbar_arrive(smem_u32(acce_bar + buf));
             mbar_wait(smem_u32(nfull_bar + ns), (sq / kTcNormSlots) & 1);
 
             u32 mask_lo = 0, mask_hi = 0;  // my survivors of this tile (bit j = score j)
@@ -559,7 +661,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
     if (warp == 5) {
         __syncwarp();
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
     }
 }
 
