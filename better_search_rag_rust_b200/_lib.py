@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbsr_b200.so")
+# BSR_LIB_VARIANT=tl selects the debug build with pipeline time stamps (csrc/Makefile, target `timeline`)
+LIB_PATH = os.path.join(_HERE, "libbsr_b200_tl.so" if os.environ.get("BSR_LIB_VARIANT") == "tl" else "libbsr_b200.so")
 
 BSR_OK = 0
 BSR_ERR_INVALID = -1

@@ -690,6 +690,19 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
         a.row_base = (u32)s->row_base;
         a.stages = stages;
         a.stage_kb = stage_kb;
+        a.timeline = nullptr;
+        a.tl_start = 0;
+#ifdef BSR_TC_TIMELINE
+        static long long* d_tl = nullptr;
+        const size_t tl_bytes = (size_t)2 * kTlTiles * 8 * sizeof(long long);
+        const bool tl_on = getenv("BSR_TC_TL") && q0 == 0;
+        if (tl_on) {
+            if (!d_tl) CU(cudaMalloc(&d_tl, tl_bytes));
+            CU(cudaMemsetAsync(d_tl, 0, tl_bytes, st));
+            a.timeline = d_tl;
+            a.tl_start = (u32)atoi(getenv("BSR_TC_TL"));
+        }
+#endif
         CU(cudaMemsetAsync(s->d_gtau.p, 0, gm_bytes, st));  // 0 < ordered(-inf): "nobody published yet"
         TRY(prof_begin(s, st));
         if (mode == 2) TRY(launch_tensor<2>(s, a, grid, smem, st));
@@ -703,6 +716,26 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
             CU(cudaGetLastError());
         }
         TRY(prof_end(s, st));
+#ifdef BSR_TC_TIMELINE
+        if (tl_on) {  // debug only: dump the pipeline stamps of CTAs 0 and 1 (cycles since CTA 0's first stamp)
+            std::vector<long long> h(2 * kTlTiles * 8);
+            CU(cudaStreamSynchronize(st));
+            CU(cudaMemcpy(h.data(), d_tl, tl_bytes, cudaMemcpyDeviceToHost));
+            for (int c = 0; c < 2; c++) {
+                const long long t0 = h[(size_t)c * kTlTiles * 8];
+                fprintf(stderr, "cta %d tile: prod_slot_free mma_acc_free mma_data_ok mma_issued | epi_wait epi_acc_ready "
+                                "epi_ld_done epi_done\n", c);
+                for (u32 t = 0; t < kTlTiles; t++) {
+                    fprintf(stderr, "%3u:", t);
+                    for (int e = 0; e < 8; e++) {
+                        const long long v = h[((size_t)c * kTlTiles + t) * 8 + e];
+                        fprintf(stderr, " %8lld", v ? v - t0 : -1);
+                    }
+                    fprintf(stderr, "\n");
+                }
+            }
+        }
+#endif
     }
     CU(cudaEventRecord(s->ev_scan1, st));
     s->scan_timed = true;

@@ -83,7 +83,22 @@ struct TensorScanArgs {
     u32 nq_valid;                // <= 128 * cluster size
     u32 n_rows, n_tiles, KB, dim, k, k_pad, row_base, stages;
     u32 stage_kb;                // 64-column blocks per ring stage (<= kTcStageKB)
+    long long* timeline;         // debug builds (-DBSR_TC_TIMELINE): [2 CTAs][kTlTiles][8] clock64 stamps
+    u32 tl_start;                // first tile (position in the CTA's sequence) the timeline records
 };
+
+// Debug timeline (tools/probe_timeline.sh): CTAs 0 and 1 stamp the pipeline events of their first
+// kTlTiles tiles.  Compiled out unless BSR_TC_TIMELINE is defined.
+constexpr u32 kTlTiles = 96;
+#ifdef BSR_TC_TIMELINE
+#define BSR_TL(sq, ev)                                                                                   \
+    do {                                                                                                 \
+        if (a.timeline && blockIdx.x < 2 && (sq) >= a.tl_start && (sq) < a.tl_start + kTlTiles)          \
+            a.timeline[((size_t)blockIdx.x * kTlTiles + ((sq) - a.tl_start)) * 8 + (ev)] = clock64();   \
+    } while (0)
+#else
+#define BSR_TL(sq, ev) do { } while (0)
+#endif
 
 // ---- tcgen05 wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -114,12 +129,16 @@ __device__ __forceinline__ u32 cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster.  Default
+// semantics on purpose: `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR in front of the
+// arrive (~2 000 cycles per tile with survivor stores in flight, measured in the pair-mode
+// epilogue).  What these arrives order is tcgen05 / TMA (async proxy) work, which the tcgen05 fences
+// and the barrier's own completion already cover.
 __device__ __forceinline__ void mbar_arrive_cluster(u32 local_bar, u32 rank) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"(local_bar), "r"(rank)
         : "memory");
 }
@@ -128,7 +147,7 @@ __device__ __forceinline__ void mbar_wait_cluster(u32 bar, u32 parity) {
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
             : "r"(bar), "r"(parity)
@@ -215,6 +234,13 @@ __device__ __forceinline__ void tmem_ld32(u32 taddr, float* v) {
         : "memory");
 }
 
+// max of three, NaN if any input is NaN (SASS FMNMX3.NAN)
+__device__ __forceinline__ float fmax3_nan(float x, float y, float z) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(x), "f"(y), "f"(z));
+    return r;
+}
+
 // order-preserving u32 image of a float (for atomicMax on class maxima); NaN never gets here
 __device__ __forceinline__ u32 f32_ordered(float f) { return ordered_from_bits(__float_as_uint(f)); }
 __device__ __forceinline__ float f32_from_ordered(u32 o) { return __uint_as_float(bits_from_ordered(o)); }
@@ -286,7 +312,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const u32 S = a.stages, KB = a.KB, SKB = a.stage_kb;
     // bytes of one 64-column block in MY shared memory: all 64 rows, or my 32 rows in pair mode
-    const u32 blk_bytes = PAIR ? kTileBytes / 2 : kTileBytes;
+    constexpr u32 kBlk = PAIR ? kTileBytes / 2 : kTileBytes;
+    const u32 blk_bytes = kBlk;
     const u32 stage_bytes = SKB * blk_bytes;
     // [ring: S stages (1024-byte aligned: swizzle atoms) | norm ring: 16 x (64 |a| + 64 1/|a|) |
     //  barriers | tmem base]
@@ -314,7 +341,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
         }
         for (u32 i = 0; i < 2; i++) {
             mbar_init(smem_u32(accf_bar + i), 1);
-            mbar_init(smem_u32(acce_bar + i), PAIR ? 2 * kTcQ : kTcQ);  // pair: both CTAs' epilogues, at the leader
+            // pair: both CTAs' epilogues arrive at the leader (the peer's with one remote arrive per warp)
+            mbar_init(smem_u32(acce_bar + i), PAIR ? kTcQ + 4 : kTcQ);
         }
         mbar_init(smem_u32(aready_bar), PAIR ? 2 * kTcQ : kTcQ);
         for (u32 i = 0; i < kTcNormSlots; i++) {
@@ -373,6 +401,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
                     // every CTA of the cluster has retired its MMAs on this slot
                     if (C > 1) mbar_wait_cluster(smem_u32(empty_bar + slot), phase ^ 1);
                     else mbar_wait(smem_u32(empty_bar + slot), phase ^ 1);
+                    if (kb0 == 0) BSR_TL(sq, 0);
                     const unsigned char* src = a.tiles + (tile * KB + kb0) * kTileBytes;
                     const u32 dst = smem_u32(ring + (size_t)slot * stage_bytes);
                     if (PAIR) {
@@ -427,29 +456,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
                 if (PAIR) mbar_wait_cluster(smem_u32(acce_bar + buf), ((li >> 1) & 1) ^ 1);
                 else mbar_wait(smem_u32(acce_bar + buf), ((li >> 1) & 1) ^ 1);
                 tc_fence_after();
+                if (lane == 0) BSR_TL(li, 1);
                 const u32 d_tmem = tmem + buf * kTcN;
                 for (u32 kb0 = 0; kb0 < KB; kb0 += SKB) {
                     mbar_wait(smem_u32(full_bar + slot), phase);
                     if (PAIR) mbar_wait_cluster(smem_u32(peerfull_bar + slot), phase);  // ... and the peer's half
                     tc_fence_after();
+                    if (lane == 0 && kb0 == 0) BSR_TL(li, 2);
                     const u32 nkb = min(SKB, KB - kb0);
                     const u32 stage_addr = smem_u32(ring + (size_t)slot * stage_bytes);
-                    for (u32 kk = 0; kk < nkb; kk++) {
-                        const u32 kb = kb0 + kk;
-                        const u64 desc = make_sw128_desc(stage_addr + kk * blk_bytes);
-                        if (elect_one()) {
+                    // One elected lane issues the whole stage.  The loop is fully unrolled with
+                    // compile-time operand offsets (descriptor + kk * block + k4 * 32 bytes, A column
+                    // + 8 per K16) so the issue stream is UTCHMMA after UTCHMMA: with run-time loop
+                    // arithmetic between them (R2UR, descriptor rebuilds) the issuing lane needed
+                    // ~45 cycles per MMA against the tensor pipe's 32 (timeline, B200).
+                    if (elect_one()) {
+                        const u64 desc0 = make_sw128_desc(stage_addr);
+                        const u32 a0 = tmem_a + kb0 * 32;
 #pragma unroll
-                            for (u32 k4 = 0; k4 < 4; k4++) {  // 4 x K16 per 64-column block
-                                if (PAIR)
-                                    tc_mma_ts_pair(d_tmem, tmem_a + (kb * 4 + k4) * 8, desc + (u64)(k4 * 2),
-                                                   kIdescBf16M256N64, (kb | k4) != 0 ? 1u : 0u);
-                                else
-                                    tc_mma_ts(d_tmem, tmem_a + (kb * 4 + k4) * 8, desc + (u64)(k4 * 2), kIdescBf16M128N64,
-                                              (kb | k4) != 0 ? 1u : 0u);
+                        for (u32 kk = 0; kk < kTcStageKB; kk++) {
+                            if (kk < nkb) {
+#pragma unroll
+                                for (u32 k4 = 0; k4 < 4; k4++) {  // 4 x K16 per 64-column block
+                                    const u32 acc = (kk | k4) != 0 ? 1u : (kb0 != 0 ? 1u : 0u);
+                                    const u64 desc = desc0 + (u64)(kk * (kBlk >> 4) + k4 * 2);
+                                    if (PAIR) tc_mma_ts_pair(d_tmem, a0 + (kk * 4 + k4) * 8, desc, kIdescBf16M256N64, acc);
+                                    else tc_mma_ts(d_tmem, a0 + (kk * 4 + k4) * 8, desc, kIdescBf16M128N64, acc);
+                                }
                             }
                         }
-                        __syncwarp();
                     }
+                    __syncwarp();
                     // slot reusable once these MMAs retire -- in every CTA that shares the stage
                     if (elect_one()) {
                         if (PAIR) tc_commit_pair_multicast(smem_u32(empty_bar + slot), both);
@@ -468,6 +505,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
                     else tc_commit(smem_u32(accf_bar + buf));
                 }
                 __syncwarp();
+                if (lane == 0) BSR_TL(li, 3);
             }
         }
     } else {
@@ -539,77 +577,115 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
             const float* na_s = s_norm + (size_t)ns * 2 * kTcN;
             const float4* inv4 = reinterpret_cast<const float4*>(na_s + kTcN);
 
+            if (tid == 0) BSR_TL(sq, 4);
             mbar_wait(smem_u32(accf_bar + buf), (sq >> 1) & 1);
             tc_fence_after();
+            if (tid == 0) BSR_TL(sq, 5);
             float v[kTcN];
             tmem_ld32(tmem + lane_addr + buf * kTcN, v);
             tmem_ld32(tmem + lane_addr + buf * kTcN + 32, v + 32);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
             // scores are in registers: free the accumulator (pair mode: at the leader, which issues)
-            if (PAIR && crank != 0) mbar_arrive_cluster(smem_u32(acce_bar + buf), 0);
-            else mbar_arrive(smem_u32(acce_bar + buf));
+            if (PAIR && crank != 0) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(smem_u32(acce_bar + buf), 0);
+            } else {
+                mbar_arrive(smem_u32(acce_bar + buf));
+            }
             mbar_wait(smem_u32(nfull_bar + ns), (sq / kTcNormSlots) & 1);
+            if (tid == 0) BSR_TL(sq, 6);
 
             u32 mask_lo = 0, mask_hi = 0;  // my survivors of this tile (bit j = score j)
-            if (active) {
-                const u32 n_here = min(kTcN, a.n_rows - row0);
-                // pass 1 -- branch-free and unrolled, so the 64 independent chains overlap: one multiply,
-                // one FMNMX, one compare per score, survivors recorded in a 64-bit mask
-                const float pass_thr = learn_only ? INFINITY : thr;
-                u32 m_lo = 0, m_hi = 0;
+            const u32 n_here = min(kTcN, a.n_rows - row0);
+            // inactive lanes (no query) never survive anything
+            const float pass_thr = (learn_only || !active) ? INFINITY : thr;
+            if (n_here < kTcN) {
+                // last tile of the store: padding rows score NaN -- FMNMX leaves the class maxima
+                // alone, the NaN forces pass 1b, and the padding bits are dropped there
 #pragma unroll
-                for (u32 j4 = 0; j4 < kTcN / 4; j4++) {
-                    const float4 iv = inv4[j4];
-                    const float ivs[4] = {iv.x, iv.y, iv.z, iv.w};
-#pragma unroll
-                    for (u32 e = 0; e < 4; e++) {
-                        const u32 j = j4 * 4 + e;
-                        const float t = v[j] * ivs[e];
-                        // rows past the end of the store never count; a NaN score leaves the maximum alone
-                        gmr[j] = fmaxf(gmr[j], j < n_here ? t : -INFINITY);
-                        const u32 bit = (!(t < pass_thr)) ? 1u : 0u;
-                        if (j < 32) m_lo |= bit << (j & 31);
-                        else m_hi |= bit << (j & 31);
-                    }
-                }
-                if (n_here < kTcN) {  // last tile of the store: drop the padding rows
-                    const u64 keep = (1ull << n_here) - 1ull;
-                    m_lo &= (u32)keep;
-                    m_hi &= (u32)(keep >> 32);
-                }
-                mask_lo = m_lo;
-                mask_hi = m_hi;
+                for (u32 j = 0; j < kTcN; j++)
+                    if (j >= n_here) v[j] = __uint_as_float(0x7FC00000u);
             }
-            // pass 2 -- visit only the score positions where SOME lane of the warp has a survivor
-            // (about two per tile): a jump table picks the register, the owning lanes append
-            {
-                u32 w_lo = __reduce_or_sync(0xFFFFFFFFu, mask_lo), w_hi = __reduce_or_sync(0xFFFFFFFFu, mask_hi);
-                while (w_lo | w_hi) {
-                    u32 j;
-                    if (w_lo) {
-                        j = __ffs(w_lo) - 1;
-                        w_lo &= w_lo - 1;
-                    } else {
-                        j = 32 + __ffs(w_hi) - 1;
-                        w_hi &= w_hi - 1;
+            // pass 1 -- branch-free and unrolled, so the 64 independent chains overlap.  Per score: one
+            // multiply, one FMNMX into its class maximum, and half a 3-input NaN-propagating FMNMX3
+            // into the best score of its 16-row group.  Only where a group's best reaches the bound
+            // (or is NaN) does the warp build that group's survivor bits (pass 1b).
+            float gmax[4];
+#pragma unroll
+            for (u32 g = 0; g < 4; g++) {
+                float m = -INFINITY;
+#pragma unroll
+                for (u32 j4 = g * 4; j4 < g * 4 + 4; j4++) {
+                    const float4 iv = inv4[j4];
+                    const float t0 = v[j4 * 4] * iv.x, t1 = v[j4 * 4 + 1] * iv.y;
+                    const float t2 = v[j4 * 4 + 2] * iv.z, t3 = v[j4 * 4 + 3] * iv.w;
+                    gmr[j4 * 4] = fmaxf(gmr[j4 * 4], t0);  // a NaN score leaves the class maximum alone
+                    gmr[j4 * 4 + 1] = fmaxf(gmr[j4 * 4 + 1], t1);
+                    gmr[j4 * 4 + 2] = fmaxf(gmr[j4 * 4 + 2], t2);
+                    gmr[j4 * 4 + 3] = fmaxf(gmr[j4 * 4 + 3], t3);
+                    m = fmax3_nan(m, t0, t1);
+                    m = fmax3_nan(m, t2, t3);
+                }
+                gmax[g] = m;
+            }
+            const float tmax = fmax3_nan(fmax3_nan(gmax[0], gmax[1], gmax[2]), gmax[3], gmax[3]);
+            // NaN scores always survive (their exact distance decides)
+            if (__any_sync(0xFFFFFFFFu, !(tmax < pass_thr))) {
+                // pass 1b -- survivor bits of the groups that can hold one
+#pragma unroll
+                for (u32 g = 0; g < 4; g++) {
+                    if (__any_sync(0xFFFFFFFFu, !(gmax[g] < pass_thr))) {
+                        u32 mm = 0;
+#pragma unroll
+                        for (u32 j4 = g * 4; j4 < g * 4 + 4; j4++) {
+                            const float4 iv = inv4[j4];
+                            const float ivs[4] = {iv.x, iv.y, iv.z, iv.w};
+#pragma unroll
+                            for (u32 e = 0; e < 4; e++) {
+                                const float t = v[j4 * 4 + e] * ivs[e];
+                                mm |= ((!(t < pass_thr)) ? 1u : 0u) << ((j4 * 4 + e) & 31);
+                            }
+                        }
+                        if (g < 2) mask_lo |= mm;
+                        else mask_hi |= mm;
                     }
-                    float sc;
-                    switch (j) {
+                }
+                if (n_here < kTcN) {  // drop the padding rows
+                    const u64 keep = (1ull << n_here) - 1ull;
+                    mask_lo &= (u32)keep;
+                    mask_hi &= (u32)(keep >> 32);
+                }
+                // pass 2 -- visit only the score positions where SOME lane of the warp has a survivor
+                // (about two per tile): a jump table picks the register, the owning lanes append
+                {
+                    u32 w_lo = __reduce_or_sync(0xFFFFFFFFu, mask_lo), w_hi = __reduce_or_sync(0xFFFFFFFFu, mask_hi);
+                    while (w_lo | w_hi) {
+                        u32 j;
+                        if (w_lo) {
+                            j = __ffs(w_lo) - 1;
+                            w_lo &= w_lo - 1;
+                        } else {
+                            j = 32 + __ffs(w_hi) - 1;
+                            w_hi &= w_hi - 1;
+                        }
+                        float sc;
+                        switch (j) {
 #define BSR_CASE(J) case J: sc = v[J]; break;
 #define BSR_CASE8(B) BSR_CASE(B) BSR_CASE(B + 1) BSR_CASE(B + 2) BSR_CASE(B + 3) BSR_CASE(B + 4) BSR_CASE(B + 5) BSR_CASE(B + 6) BSR_CASE(B + 7)
-                        BSR_CASE8(0) BSR_CASE8(8) BSR_CASE8(16) BSR_CASE8(24) BSR_CASE8(32) BSR_CASE8(40) BSR_CASE8(48)
-                        BSR_CASE8(56)
+                            BSR_CASE8(0) BSR_CASE8(8) BSR_CASE8(16) BSR_CASE8(24) BSR_CASE8(32) BSR_CASE8(40) BSR_CASE8(48)
+                            BSR_CASE8(56)
 #undef BSR_CASE8
 #undef BSR_CASE
-                        default: sc = 0.0f; break;
-                    }
-                    if (((j < 32 ? mask_lo : mask_hi) >> (j & 31)) & 1u) {
-                        surv_buf[surv_cnt++] = pack_survivor(row0 + j, sc);
-                        if (surv_cnt == kTcSurvivorCap) {
-                            // overflow (adversarial row order only): keep the exact best k
-                            compact_survivors(a, surv_buf, surv_cnt, qp, mag_b, surv_buf + kTcSurvivorCap);
-                            surv_cnt = a.k;
+                            default: sc = 0.0f; break;
+                        }
+                        if (((j < 32 ? mask_lo : mask_hi) >> (j & 31)) & 1u) {
+                            surv_buf[surv_cnt++] = pack_survivor(row0 + j, sc);
+                            if (surv_cnt == kTcSurvivorCap) {
+                                // overflow (adversarial row order only): keep the exact best k
+                                compact_survivors(a, surv_buf, surv_cnt, qp, mag_b, surv_buf + kTcSurvivorCap);
+                                surv_cnt = a.k;
+                            }
                         }
                     }
                 }
@@ -619,8 +695,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
             if (active && !tiny_q) {
                 // merge my class maxima with everyone else's and refresh the bound.  The bound improves
                 // like log(rows seen): refresh densely while it is young, then every 8 / 32 / 128 tiles
-                const u32 every = sq < 64 ? 8u : (sq < 512 ? 32u : 128u);
-                const bool refresh = (sq + 1 == learn) || (sq >= learn && sq < learn + 8) || ((sq + 1) % every == 0);
+                const u32 every = sq < 64 ? 8u : (sq < 512 ? 32u : 128u);  // powers of two
+                const bool refresh = (sq + 1 == learn) || (sq >= learn && sq < learn + 8) || (((sq + 1) & (every - 1)) == 0);
                 if (refresh) {
                     float bound = INFINITY;
                     for (u32 c0 = 0; c0 < kc; c0 += kTcN) {  // one 64-class group at a time
@@ -647,6 +723,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
                     thr = (bound == -INFINITY) ? -INFINITY : bound - 1e-6f * mag_b - 1e-6f * fabsf(bound);
                 }
             }
+            if (tid == 0) BSR_TL(sq, 7);
         }
         // exact keys + sort of the survivors happen in finalize_survivors_kernel (fully parallel)
         if (active) {
