@@ -651,7 +651,7 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
     const u32 n_tiles = (u32)((s->n_rows + kTcN - 1) / kTcN);
     // more than one 128-query group: clusters of 2 CTAs share every store tile (TMA multicast)
     // mode 0: single CTAs; 1: clusters of 2 with multicast tiles; 2: CTA pairs (cta_group::2)
-    u32 mode = (nq > kTcQ && s->n_sm >= 2) ? 1u : 0u;  // measured: multicast (1) beats pairs (2) by ~6 %
+    u32 mode = (nq > kTcQ && s->n_sm >= 2) ? 2u : 0u;  // measured: pairs (2) beat multicast (1) by ~6 %
     if (const char* e = getenv("BSR_TENSOR_MODE")) mode = (u32)std::min(2, std::max(0, atoi(e)));
     const u32 C = mode == 0 ? 1u : 2u;
     const unsigned n_clusters = std::max(1u, std::min<unsigned>((unsigned)s->n_sm / C, n_tiles));

@@ -241,6 +241,16 @@ __device__ __forceinline__ float fmax3_nan(float x, float y, float z) {
     return r;
 }
 
+// predicated fire-and-forget atomic max (SASS @P REDG.MAX): no branch around it
+__device__ __forceinline__ void red_max_if(u32* addr, u32 val, bool pred) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %2, 0;\n\t"
+        "@p red.global.max.u32 [%0], %1;\n\t}"
+        ::"l"(addr), "r"(val), "r"((u32)pred)
+        : "memory");
+}
+
 // order-preserving u32 image of a float (for atomicMax on class maxima); NaN never gets here
 __device__ __forceinline__ u32 f32_ordered(float f) { return ordered_from_bits(__float_as_uint(f)); }
 __device__ __forceinline__ float f32_from_ordered(u32 o) { return __uint_as_float(bits_from_ordered(o)); }
@@ -566,6 +576,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
         u64* surv_buf = a.survivors + ((size_t)q * n_clusters + cluster_id) * (2 * kTcSurvivorCap);
         u32 surv_cnt = 0;
         float thr = -INFINITY;    // prune rows with t < thr, t = S / |a|
+        u32 next_refresh = max(learn, 1u);  // refresh the bound after this many tiles of the sequence
 
         for (u32 sq = 0; sq < n_seq; sq++) {
             const u32 buf = sq & 1;
@@ -596,7 +607,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
             mbar_wait(smem_u32(nfull_bar + ns), (sq / kTcNormSlots) & 1);
             if (tid == 0) BSR_TL(sq, 6);
 
-            u32 mask_lo = 0, mask_hi = 0;  // my survivors of this tile (bit j = score j)
             const u32 n_here = min(kTcN, a.n_rows - row0);
             // inactive lanes (no query) never survive anything
             const float pass_thr = (learn_only || !active) ? INFINITY : thr;
@@ -632,59 +642,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
             const float tmax = fmax3_nan(fmax3_nan(gmax[0], gmax[1], gmax[2]), gmax[3], gmax[3]);
             // NaN scores always survive (their exact distance decides)
             if (__any_sync(0xFFFFFFFFu, !(tmax < pass_thr))) {
-                // pass 1b -- survivor bits of the groups that can hold one
+                // pass 2 -- only the 16-row groups where some lane of the warp can have a survivor:
+                // re-test each score and append the survivors (compile-time register index, predicated
+                // stores: no per-survivor loop, no register select)
+                const u32 n_mine = active ? n_here : 0u;  // padding rows and idle lanes never append
 #pragma unroll
                 for (u32 g = 0; g < 4; g++) {
                     if (__any_sync(0xFFFFFFFFu, !(gmax[g] < pass_thr))) {
-                        u32 mm = 0;
+                        if (surv_cnt + 16 > kTcSurvivorCap) {
+                            // overflow (adversarial row order only): keep the exact best k
+                            compact_survivors(a, surv_buf, surv_cnt, qp, mag_b, surv_buf + kTcSurvivorCap);
+                            surv_cnt = a.k;
+                        }
 #pragma unroll
                         for (u32 j4 = g * 4; j4 < g * 4 + 4; j4++) {
                             const float4 iv = inv4[j4];
                             const float ivs[4] = {iv.x, iv.y, iv.z, iv.w};
 #pragma unroll
                             for (u32 e = 0; e < 4; e++) {
-                                const float t = v[j4 * 4 + e] * ivs[e];
-                                mm |= ((!(t < pass_thr)) ? 1u : 0u) << ((j4 * 4 + e) & 31);
-                            }
-                        }
-                        if (g < 2) mask_lo |= mm;
-                        else mask_hi |= mm;
-                    }
-                }
-                if (n_here < kTcN) {  // drop the padding rows
-                    const u64 keep = (1ull << n_here) - 1ull;
-                    mask_lo &= (u32)keep;
-                    mask_hi &= (u32)(keep >> 32);
-                }
-                // pass 2 -- visit only the score positions where SOME lane of the warp has a survivor
-                // (about two per tile): a jump table picks the register, the owning lanes append
-                {
-                    u32 w_lo = __reduce_or_sync(0xFFFFFFFFu, mask_lo), w_hi = __reduce_or_sync(0xFFFFFFFFu, mask_hi);
-                    while (w_lo | w_hi) {
-                        u32 j;
-                        if (w_lo) {
-                            j = __ffs(w_lo) - 1;
-                            w_lo &= w_lo - 1;
-                        } else {
-                            j = 32 + __ffs(w_hi) - 1;
-                            w_hi &= w_hi - 1;
-                        }
-                        float sc;
-                        switch (j) {
-#define BSR_CASE(J) case J: sc = v[J]; break;
-#define BSR_CASE8(B) BSR_CASE(B) BSR_CASE(B + 1) BSR_CASE(B + 2) BSR_CASE(B + 3) BSR_CASE(B + 4) BSR_CASE(B + 5) BSR_CASE(B + 6) BSR_CASE(B + 7)
-                            BSR_CASE8(0) BSR_CASE8(8) BSR_CASE8(16) BSR_CASE8(24) BSR_CASE8(32) BSR_CASE8(40) BSR_CASE8(48)
-                            BSR_CASE8(56)
-#undef BSR_CASE8
-#undef BSR_CASE
-                            default: sc = 0.0f; break;
-                        }
-                        if (((j < 32 ? mask_lo : mask_hi) >> (j & 31)) & 1u) {
-                            surv_buf[surv_cnt++] = pack_survivor(row0 + j, sc);
-                            if (surv_cnt == kTcSurvivorCap) {
-                                // overflow (adversarial row order only): keep the exact best k
-                                compact_survivors(a, surv_buf, surv_cnt, qp, mag_b, surv_buf + kTcSurvivorCap);
-                                surv_cnt = a.k;
+                                const u32 j = j4 * 4 + e;
+                                const float t = v[j] * ivs[e];
+                                if (!(t < pass_thr) && j < n_mine) surv_buf[surv_cnt++] = pack_survivor(row0 + j, v[j]);
                             }
                         }
                     }
@@ -692,31 +670,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
             }
             mbar_arrive(smem_u32(nempty_bar + ns));  // norm block consumed
 
-            if (active && !tiny_q) {
-                // merge my class maxima with everyone else's and refresh the bound.  The bound improves
-                // like log(rows seen): refresh densely while it is young, then every 8 / 32 / 128 tiles
-                const u32 every = sq < 64 ? 8u : (sq < 512 ? 32u : 128u);  // powers of two
-                const bool refresh = (sq + 1 == learn) || (sq >= learn && sq < learn + 8) || (((sq + 1) & (every - 1)) == 0);
-                if (refresh) {
+            if (sq + 1 == next_refresh) {
+                // Merge my class maxima with everyone else's and refresh the bound.  The bound improves
+                // like log(rows seen), so the refresh points are spaced geometrically (x 1.5).  Branch-free:
+                // 64 coalesced L2 reads per class group, a predicated RED.MAX per improved class.
+                next_refresh = max(next_refresh + 1, next_refresh + (next_refresh >> 1));
+                if (active && !tiny_q) {
                     float bound = INFINITY;
                     for (u32 c0 = 0; c0 < kc; c0 += kTcN) {  // one 64-class group at a time
                         u32 their_bits[kTcN];
 #pragma unroll
                         for (u32 i = 0; i < kTcN; i++) their_bits[i] = __ldcg(g_gm + (size_t)(c0 + i) * QS);  // independent, coalesced L2 reads
-                        const bool mine_group = (c0 == group * kTcN);
+                        if (c0 == group * kTcN) {  // the group this CTA contributes to
 #pragma unroll
-                        for (u32 i = 0; i < kTcN; i++) {
-                            // 0 = nobody has published this class yet
-                            float best = their_bits[i] ? f32_from_ordered(their_bits[i]) : -INFINITY;
-                            if (mine_group) {
-                                if (gmr[i] > best) {
-                                    atomicMax(g_gm + (size_t)(c0 + i) * QS, f32_ordered(gmr[i]));
-                                    best = gmr[i];
-                                } else {
-                                    gmr[i] = best;
-                                }
+                            for (u32 i = 0; i < kTcN; i++) {
+                                // 0 = nobody has published this class yet
+                                const float best = their_bits[i] ? f32_from_ordered(their_bits[i]) : -INFINITY;
+                                red_max_if(g_gm + (size_t)(c0 + i) * QS, f32_ordered(gmr[i]), gmr[i] > best);
+                                gmr[i] = fmaxf(gmr[i], best);
+                                bound = fminf(bound, gmr[i]);
                             }
-                            bound = fminf(bound, best);
+                        } else {
+#pragma unroll
+                            for (u32 i = 0; i < kTcN; i++)
+                                bound = fminf(bound, their_bits[i] ? f32_from_ordered(their_bits[i]) : -INFINITY);
                         }
                     }
                     // kc >= k distinct rows reach `bound`; keep a 1e-6 (in similarity) safety margin
