@@ -506,17 +506,22 @@ static int scan_variant() {
     return v;
 }
 
-static size_t bulk_smem_bytes(const bsr_store* s, u32 K, u32 stages, u32 qb) {
-    return (size_t)kBulkWarps * stages * kChunkBytes + (size_t)qb * s->dq * sizeof(float4) +
-           (size_t)qb * kBulkWarps * K * sizeof(u64) + (size_t)kBulkWarps * stages * sizeof(u64);
+static size_t bulk_smem_bytes(const bsr_store* s, u32 K, u32 stages, u32 qb, u32 active_warps = kBulkWarps,
+                              u32 W = kBulkWarps) {
+    return (size_t)active_warps * stages * kChunkBytes + (size_t)qb * s->dq * sizeof(float4) +
+           (size_t)qb * W * K * sizeof(u64) + (size_t)W * stages * sizeof(u64);
 }
 
-static u32 bulk_stages(const bsr_store* s, u32 K, u32 qb) {
-    // 3 stages x 4 KiB x 8 warps = 96 KiB in flight per SM measured fastest on B200 (deeper rings
-    // lose bandwidth: 6 stages -7 %); BSR_BULK_STAGES overrides for tuning.
-    u32 st = 3;
+// Ring depth per warp.  Large stores: 3 stages x 4 KiB x 8 warps = 96 KiB in flight per SM measured
+// fastest on B200 (deeper rings lose bandwidth: 6 stages -7 %).  Small stores (at most two panels
+// per warp) are latency-bound -- a warp's panel is 24 chunks, i.e. 8 dependent round trips through a
+// 3-stage ring -- so they get as deep a ring as fits, up to a whole panel in flight per warp; the
+// ring is only allocated for the warps that own a panel.  BSR_BULK_STAGES overrides for tuning.
+static u32 bulk_stages(const bsr_store* s, u32 K, u32 qb, u32 active_warps = kBulkWarps, bool small = false,
+                       u32 W = kBulkWarps) {
+    u32 st = small ? 24 : 3;
     if (const char* e = getenv("BSR_BULK_STAGES")) st = std::max(2, atoi(e));
-    while (st >= 2 && bulk_smem_bytes(s, K, st, qb) + 1024 > s->smem_optin) st--;
+    while (st >= 2 && bulk_smem_bytes(s, K, st, qb, active_warps, W) + 1024 > s->smem_optin) st--;
     return st;  // < 2: does not fit
 }
 
@@ -529,32 +534,33 @@ static u32 bulk_max_qb(const bsr_store* s, u32 K) {
     return 1;
 }
 
-template <int QB, bool BF16>
-static int launch_scan_bulk_t(bsr_store* s, const ScanArgs& a, unsigned grid, u32 stages,
+template <int QB, bool BF16, int W = kBulkWarps>
+static int launch_scan_bulk_t(bsr_store* s, const ScanArgs& a, unsigned grid, u32 stages, u32 active_warps,
                               cudaStream_t st) {
     static thread_local bool configured[64] = {false};
     if (!configured[s->device & 63]) {
         cudaFuncAttributes fa;
-        CU(cudaFuncGetAttributes(&fa, scan_topk_bulk_kernel<QB, BF16>));
-        CU(cudaFuncSetAttribute(scan_topk_bulk_kernel<QB, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CU(cudaFuncGetAttributes(&fa, scan_topk_bulk_kernel<QB, BF16, W>));
+        CU(cudaFuncSetAttribute(scan_topk_bulk_kernel<QB, BF16, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(s->smem_optin - fa.sharedSizeBytes)));
         configured[s->device & 63] = true;
     }
     BulkScanArgs ba;
     ba.s = a;
     ba.stages = stages;
-    scan_topk_bulk_kernel<QB, BF16>
-        <<<grid, kBulkThreads, bulk_smem_bytes(s, a.k_pad, stages, QB), st>>>(ba);
+    ba.active_warps = active_warps;
+    scan_topk_bulk_kernel<QB, BF16, W>
+        <<<grid, W * 32, bulk_smem_bytes(s, a.k_pad, stages, QB, active_warps, W), st>>>(ba);
     s->launches++;
     CU(cudaGetLastError());
     return BSR_OK;
 }
 
 template <int QB>
-static int launch_scan_bulk(bsr_store* s, const ScanArgs& a, unsigned grid, u32 stages,
+static int launch_scan_bulk(bsr_store* s, const ScanArgs& a, unsigned grid, u32 stages, u32 active_warps,
                             cudaStream_t st) {
-    return is_bf16(s) ? launch_scan_bulk_t<QB, true>(s, a, grid, stages, st)
-                      : launch_scan_bulk_t<QB, false>(s, a, grid, stages, st);
+    return is_bf16(s) ? launch_scan_bulk_t<QB, true>(s, a, grid, stages, active_warps, st)
+                      : launch_scan_bulk_t<QB, false>(s, a, grid, stages, active_warps, st);
 }
 
 // reduce n_lists lists per query to one; returns the buffer holding [nq][K] in *result
@@ -757,7 +763,15 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
     const u32 n_panels = (u32)((s->n_rows + 31) / 32);
     const bool bulk = (scan_variant() == 1 || is_bf16(s)) && bulk_stages(s, K, 1) >= 2;
     CHECK(bulk || !is_bf16(s), BSR_ERR_UNSUPPORTED, "search: BF16 stores need the bulk-async scan kernel");
-    const unsigned grid = scan_grid(s, n_panels, bulk ? kBulkWarps : kScanWarps);
+    // bulk kernel: one CTA per SM, or one per panel when the store has fewer panels than SMs
+    const unsigned grid = bulk ? std::max(1u, std::min<unsigned>((unsigned)s->n_sm, n_panels))
+                               : scan_grid(s, n_panels, kScanWarps);
+    // small stores (more than one, at most four rounds of panels at 8 warps per CTA): 16 warps per CTA
+    const u32 per_cta = (n_panels + grid - 1) / grid;
+    const bool wide = bulk && per_cta > (u32)kBulkWarps && per_cta <= 4u * kBulkWarps &&
+                      bulk_stages(s, K, 1, std::min<u32>(16, per_cta), true, 16) >= 2 && !getenv("BSR_NO_WIDE");
+    const u32 active_warps = std::min<u32>(wide ? 16u : (u32)kBulkWarps, per_cta);
+    const bool small_store = n_panels <= 2u * grid * (wide ? 16u : (u32)kBulkWarps);
     const size_t smem = (size_t)s->dq * sizeof(float4) + (size_t)kScanWarps * K * sizeof(u64);
     CHECK(bulk || smem + 1024 <= s->smem_optin, BSR_ERR_UNSUPPORTED,
           "search: dim %u with top_k %u needs %zu bytes of shared memory (limit %zu)", s->dim, k,
@@ -798,13 +812,37 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
         a.fin.idx = d_idx ? d_idx + (size_t)q * k : nullptr;
         a.fin.dist = d_idx ? d_dist + (size_t)q * k : nullptr;
         a.fin.count = d_idx ? d_count + q : nullptr;
+        a.dbg = a.fin.dbg = nullptr;
+#ifdef BSR_TC_TIMELINE
+        static unsigned long long* d_dbg = nullptr;
+        static unsigned long long* h_dbg = nullptr;  // pinned, also stamped by the host
+        const bool dbg_on = getenv("BSR_SCAN_TL") != nullptr;
+        if (dbg_on) {
+            if (!d_dbg) {
+                CU(cudaMalloc(&d_dbg, 64 * sizeof(unsigned long long)));
+                CU(cudaMallocHost(&h_dbg, 64 * sizeof(unsigned long long)));
+            }
+            CU(cudaMemsetAsync(d_dbg, 0, 64 * sizeof(unsigned long long), st));
+            CU(cudaStreamSynchronize(st));
+            a.dbg = a.fin.dbg = d_dbg;
+        }
+#endif
         TRY(prof_begin(s, st));
         if (bulk) {
-            const u32 stages = bulk_stages(s, K, qb);
-            if (qb == 8) TRY(launch_scan_bulk<8>(s, a, grid, stages, st));
-            else if (qb == 4) TRY(launch_scan_bulk<4>(s, a, grid, stages, st));
-            else if (qb == 2) TRY(launch_scan_bulk<2>(s, a, grid, stages, st));
-            else TRY(launch_scan_bulk<1>(s, a, grid, stages, st));
+            if (qb == 1 && wide) {
+                const u32 stages = bulk_stages(s, K, 1, active_warps, small_store, 16);
+                if (is_bf16(s)) TRY((launch_scan_bulk_t<1, true, 16>(s, a, grid, stages, active_warps, st)));
+                else TRY((launch_scan_bulk_t<1, false, 16>(s, a, grid, stages, active_warps, st)));
+                TRY(prof_end(s, st));
+                q += qb;
+                continue;
+            }
+            const u32 aw8 = std::min<u32>(kBulkWarps, active_warps);
+            const u32 stages = bulk_stages(s, K, qb, aw8, n_panels <= 2u * grid * kBulkWarps);
+            if (qb == 8) TRY(launch_scan_bulk<8>(s, a, grid, stages, aw8, st));
+            else if (qb == 4) TRY(launch_scan_bulk<4>(s, a, grid, stages, aw8, st));
+            else if (qb == 2) TRY(launch_scan_bulk<2>(s, a, grid, stages, aw8, st));
+            else TRY(launch_scan_bulk<1>(s, a, grid, stages, aw8, st));
         } else if (s->dq % 16 == 0 && getenv("BSR_LDG_U") && atoi(getenv("BSR_LDG_U")) == 16)
             TRY(launch_scan<16>(s, a, grid, smem, st));
         else if (s->dq % 8 == 0 && !(getenv("BSR_LDG_U") && atoi(getenv("BSR_LDG_U")) == 4))
@@ -813,6 +851,21 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
         else if (s->dq % 2 == 0) TRY(launch_scan<2>(s, a, grid, smem, st));
         else TRY(launch_scan<1>(s, a, grid, smem, st));
         TRY(prof_end(s, st));
+#ifdef BSR_TC_TIMELINE
+        if (dbg_on) {
+            CU(cudaStreamSynchronize(st));
+            CU(cudaMemcpy(h_dbg, d_dbg, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            static const char* names[] = {"cta0 start", "cta0 staged", "cta0 sync", "cta0 first chunk", "cta0 panels done",
+                                          "cta0 topk finish", "cta0 lists published", "cta0 ticket", "last: start",
+                                          "last: lists folded", "last: done"};
+            fprintf(stderr, "scan timeline (ns since cta0 start), grid %u:", grid);
+            for (int i = 0; i < 11; i++) fprintf(stderr, " [%s %lld]", names[i], h_dbg[i] ? (long long)(h_dbg[i] - h_dbg[0]) : -1LL);
+            fprintf(stderr, "\n  chunk wait->ready:");
+            for (int i = 0; i < 24; i++)
+                fprintf(stderr, " %lld->%lld", (long long)(h_dbg[16 + 2 * i] - h_dbg[0]), (long long)(h_dbg[17 + 2 * i] - h_dbg[0]));
+            fprintf(stderr, "\n");
+        }
+#endif
         q += qb;
     }
     CU(cudaEventRecord(s->ev_scan1, st));

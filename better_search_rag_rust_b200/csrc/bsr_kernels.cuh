@@ -327,7 +327,20 @@ struct FinalOut {
     u64* idx;           // [nq][k]  or nullptr
     float* dist;        // [nq][k]
     u32* count;         // [nq]
+    unsigned long long* dbg;  // debug stamps (see ScanArgs::dbg)
 };
+
+#ifdef BSR_TC_TIMELINE
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// CTA 0 thread 0 stamps slots 0-7; the last CTA to finish stamps 8-11 (see scan_epilogue)
+#define BSR_STAMP(dbg, cond, slot) do { if ((dbg) && (cond)) (dbg)[slot] = globaltimer_ns(); } while (0)
+#else
+#define BSR_STAMP(dbg, cond, slot) do { } while (0)
+#endif
 
 // End of a scan CTA that handled NQ queries: for each query reduce the W per-warp lists
 // (lists[q][w][K] in shared memory) to the CTA's best K and publish them to
@@ -354,33 +367,42 @@ __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta
             for (u32 j = tid; j < K; j += W * 32) cta_keys[q * q_stride + (size_t)blockIdx.x * K + j] = ql[j];
         }
     }
+    BSR_STAMP(fo.dbg, blockIdx.x == 0 && tid == 0, 6);
     if (!fuse_final) return;
 
     __threadfence();
     __syncthreads();
     if (tid == 0) s_is_last = (atomicAdd(fo.done_counter, 1u) == gridDim.x - 1) ? 1u : 0u;
     __syncthreads();
+    BSR_STAMP(fo.dbg, blockIdx.x == 0 && tid == 0, 7);
     if (!s_is_last) return;
+    BSR_STAMP(fo.dbg, tid == 0, 8);
     __threadfence();
     // K == 32: every warp folds a strided subset of the CTA lists in registers, per query
     for (int q = 0; q < NQ; q++) {
         u64 v = kKeyMax;
         const u64* src = cta_keys + q * q_stride;
-        // this warp's lists are l = warp, warp+W, ...: fetch eight at a time (independent L2 reads,
-        // one round trip) and only then run the dependent merges
-        for (u32 l0 = warp; l0 < gridDim.x; l0 += 8 * W) {
-            u64 t[8];
+        // this warp's lists are l = warp, warp+W, ...: fetch up to 20 at a time (independent L2
+        // reads, one round trip for a grid of <= 160 CTAs at W = 8) and only then run the dependent
+        // merges; a list whose best key is not below the current 32nd best is skipped
+        for (u32 l0 = warp; l0 < gridDim.x; l0 += 20 * W) {
+            u64 t[20];
 #pragma unroll
-            for (u32 i = 0; i < 8; i++) {
+            for (u32 i = 0; i < 20; i++) {
                 const u32 l = l0 + i * W;
                 t[i] = l < gridDim.x ? ldcg_u64(src + (size_t)l * 32 + lane) : kKeyMax;
             }
 #pragma unroll
-            for (u32 i = 0; i < 8; i++) v = warp_merge32(v, t[i], lane);
+            for (u32 i = 0; i < 20; i++) {
+                const u64 their_best = __shfl_sync(0xFFFFFFFFu, t[i], 0);
+                const u64 my_worst = __shfl_sync(0xFFFFFFFFu, v, 31);
+                if (their_best < my_worst) v = warp_merge32(v, t[i], lane);
+            }
         }
         lists[((size_t)q * W + warp) * 32 + lane] = v;
     }
     __syncthreads();
+    BSR_STAMP(fo.dbg, tid == 0, 9);
     for (int q = warp; q < NQ; q += W) {
         u64 v = lists[((size_t)q * W) * 32 + lane];
 #pragma unroll
@@ -397,6 +419,7 @@ __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta
         }
     }
     if (tid == 0) *fo.done_counter = 0;
+    BSR_STAMP(fo.dbg, tid == 0, 10);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -413,6 +436,7 @@ struct ScanArgs {
     u32 row_base;          // global index of local row 0
     u32 fuse_final;        // 1: the last CTA also merges all CTA lists (requires k_pad == 32)
     FinalOut fin;
+    unsigned long long* dbg;  // debug builds (-DBSR_TC_TIMELINE): globaltimer stamps, else unused
 };
 
 template <int U>
@@ -563,24 +587,28 @@ __device__ __forceinline__ void bulk_g2s(u32 dst, const void* src, u32 bytes, u3
 
 struct BulkScanArgs {
     ScanArgs s;
-    u32 stages;  // ring depth per warp (>= 2)
+    u32 stages;        // ring depth per warp (>= 2)
+    u32 active_warps;  // warps per CTA that own at least one panel (the ring is sized for these)
 };
 
 // QB queries share one pass over the store: the row chunk is read from shared memory once and
 // feeds QB independent sequential dot products (a.query -> [QB][dim], outputs indexed by query).
 // BF16 selects the tiled bf16 layout (a.panels is then the tile base, a.dq = 16 * KB); the
 // arithmetic is the same sequential binary32 fold over the widened bf16 values.
-template <int QB, bool BF16>
-__global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_bulk_kernel(const BulkScanArgs ba) {
+// W = warps per CTA: 8 (default), or 16 for small stores, where a second round of panels on a few
+// warps would otherwise double the (latency-bound) run time.
+template <int QB, bool BF16, int W = kBulkWarps>
+__global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkScanArgs ba) {
     const ScanArgs& a = ba.s;
     constexpr int CH = kChunkQuads;                    // fp32: column-quads per 4 KiB chunk
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    BSR_STAMP(a.dbg, blockIdx.x == 0 && threadIdx.x == 0, 0);
     const u32 dq = a.dq, S = ba.stages, K = a.k_pad;
-    // [ring: W*S*4KiB | queries: QB*dq*16 | lists: QB*W*K*8 | mbarriers: W*S*8]
+    // [ring: active_warps*S*4KiB | queries: QB*dq*16 | lists: QB*W*K*8 | mbarriers: W*S*8]
     unsigned char* ring_all = smem_raw;
-    float4* sq = reinterpret_cast<float4*>(ring_all + (size_t)kBulkWarps * S * kChunkBytes);
+    float4* sq = reinterpret_cast<float4*>(ring_all + (size_t)ba.active_warps * S * kChunkBytes);
     u64* lists = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(sq) + (size_t)QB * dq * 16);
-    u64* bars = lists + (size_t)QB * kBulkWarps * K;
+    u64* bars = lists + (size_t)QB * W * K;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned char* ring_b = ring_all + (size_t)warp * S * kChunkBytes;
@@ -588,8 +616,11 @@ __global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_bulk_kernel(const B
     const u32 bar0 = smem_u32(bars + (size_t)warp * S);
     const unsigned char* store_b = reinterpret_cast<const unsigned char*>(a.panels);
 
-    const u32 total_warps = gridDim.x * kBulkWarps;
-    const u32 panel0 = blockIdx.x * kBulkWarps + warp;
+    // panels are dealt round-robin over CTAs first, then over the warps of a CTA: when the panel
+    // count is not a multiple of the warp count the extra panels spread over all SMs (each SM's
+    // share of HBM bandwidth is what bounds it), and a small store uses as many SMs as it has panels
+    const u32 total_warps = gridDim.x * W;
+    const u32 panel0 = warp * gridDim.x + blockIdx.x;
     const u32 KB = dq >> 4;                                      // bf16: 64-column blocks
     const u32 cpp = BF16 ? KB : (dq + CH - 1) / CH;              // chunks per 32-row panel
     const u32 my_panels = panel0 < a.n_panels ? (a.n_panels - 1 - panel0) / total_warps + 1 : 0;
@@ -627,7 +658,7 @@ __global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_bulk_kernel(const B
     }
 
     // stage the queries, zero-padded to the padded column count
-    for (u32 t = tid; t < (u32)QB * dq; t += kBulkThreads) {
+    for (u32 t = tid; t < (u32)QB * dq; t += (W * 32)) {
         const u32 b = t / dq, j = t - b * dq, c = 4 * j;
         const float* qp = a.query + (size_t)b * a.dim;
         float4 v;
@@ -639,8 +670,10 @@ __global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_bulk_kernel(const B
     }
     WarpTopK top[QB];
 #pragma unroll
-    for (int b = 0; b < QB; b++) top[b].init(lists + ((size_t)b * kBulkWarps + warp) * K, a.k, K, lane);
+    for (int b = 0; b < QB; b++) top[b].init(lists + ((size_t)b * W + warp) * K, a.k, K, lane);
+    BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 1);
     __syncthreads();
+    BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 2);
 
     // |b| per query: accumulated by every thread during its first panel (src/metrics.rs:155)
     float mag_b[QB], qsq[QB], acc[QB];
@@ -650,7 +683,9 @@ __global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_bulk_kernel(const B
 
     u32 stage = 0, parity = 0, ci = 0, panel = panel0;
     float mag_a = 0.0f;
-    unsigned maybe_mask = 0;  // bit b: the first columns of my row match query b
+    // bit b: every column of my row seen so far is within 1e-10 of query b's.  Seeded from the first
+    // columns of a panel, cleared chunk by chunk (only lanes with a live bit run the compare)
+    unsigned maybe_mask = 0;
     for (u32 c = 0; c < n_chunks; c++) {
         if (ci == 0) {
             const u32 row = panel * kPanelRows + lane;
@@ -658,7 +693,10 @@ __global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_bulk_kernel(const B
 #pragma unroll
             for (int b = 0; b < QB; b++) acc[b] = 0.0f;
         }
+        BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0 && c < 24, 16 + 2 * c);
         mbar_wait(bar0 + stage * 8, parity);
+        BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0 && c < 24, 17 + 2 * c);
+        BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0 && c == 0, 3);
         if (BF16) {
             // my row inside the 4 KiB half tile: atom lane/8, row lane%8; chunk c at (c ^ row%8)
             const unsigned char* rp = ring_b + (size_t)stage * kChunkBytes + (lane >> 3) * 1024 + (lane & 7) * 128;
@@ -680,6 +718,13 @@ __global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_bulk_kernel(const B
                     acc[b] = dot8_seq_bf16(acc[b], v, qa, qb2);
                     if (need_qnorm) qsq[b] = sq4_seq(sq4_seq(qsq[b], qa), qb2);
                 }
+                if (maybe_mask) {  // rare: my row has matched a query on every column so far
+#pragma unroll
+                    for (int b = 0; b < QB; b++)
+                        if (((maybe_mask >> b) & 1u) &&
+                            differs8_bf16(v, sq[b * dq + q0i + 2 * cc], sq[b * dq + q0i + 2 * cc + 1]))
+                            maybe_mask &= ~(1u << b);
+                }
             }
         } else {
             const u32 j0 = ci * CH;
@@ -694,16 +739,32 @@ __global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_bulk_kernel(const B
 #pragma unroll
                     for (int b = 0; b < QB; b++) maybe_mask |= differs4(v[0], sq[b * dq]) ? 0u : (1u << b);
                 }
-#pragma unroll
-                for (int u = 0; u < CH; u++) {
-#pragma unroll
-                    for (int b = 0; b < QB; b++) acc[b] = dot4_seq(acc[b], v[u], sq[b * dq + j0 + u]);
-                }
-                if (need_qnorm) {
+                if (need_qnorm) {  // first panel: the |b| chain runs interleaved with the dot chain
 #pragma unroll
                     for (int u = 0; u < CH; u++) {
 #pragma unroll
-                        for (int b = 0; b < QB; b++) qsq[b] = sq4_seq(qsq[b], sq[b * dq + j0 + u]);
+                        for (int b = 0; b < QB; b++) {
+                            const float4 q = sq[b * dq + j0 + u];
+                            acc[b] = dot4_seq(acc[b], v[u], q);
+                            qsq[b] = sq4_seq(qsq[b], q);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < CH; u++) {
+#pragma unroll
+                        for (int b = 0; b < QB; b++) acc[b] = dot4_seq(acc[b], v[u], sq[b * dq + j0 + u]);
+                    }
+                }
+                if (maybe_mask) {  // rare: my row has matched a query on every column so far
+#pragma unroll
+                    for (int b = 0; b < QB; b++) {
+                        if ((maybe_mask >> b) & 1u) {
+                            bool d = false;
+#pragma unroll
+                            for (int u = 0; u < CH; u++) d |= differs4(v[u], sq[b * dq + j0 + u]);
+                            if (d) maybe_mask &= ~(1u << b);
+                        }
                     }
                 }
             } else if (j0 + CH <= dq) {
@@ -723,6 +784,11 @@ __global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_bulk_kernel(const B
                         acc[b] = dot4_seq(acc[b], v, q);
                         if (need_qnorm) qsq[b] = sq4_seq(qsq[b], q);
                     }
+                    if (maybe_mask) {
+#pragma unroll
+                        for (int b = 0; b < QB; b++)
+                            if (((maybe_mask >> b) & 1u) && differs4(v, sq[b * dq + j0 + u])) maybe_mask &= ~(1u << b);
+                    }
                 }
             } else {
                 for (u32 u = 0; j0 + u < dq; u++) {
@@ -735,6 +801,7 @@ __global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_bulk_kernel(const B
                         }
                         acc[b] = dot4_seq(acc[b], v, sq[b * dq + j0 + u]);
                         if (need_qnorm) qsq[b] = sq4_seq(qsq[b], sq[b * dq + j0 + u]);
+                        if (((maybe_mask >> b) & 1u) && differs4(v, sq[b * dq + j0 + u])) maybe_mask &= ~(1u << b);
                     }
                 }
             }
@@ -752,12 +819,8 @@ __global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_bulk_kernel(const B
             const bool valid = row < a.n_rows;
 #pragma unroll
             for (int b = 0; b < QB; b++) {
-                const bool maybe = valid && ((maybe_mask >> b) & 1u);
-                const bool identical =
-                    BF16 ? warp_confirm_identical_bf16(maybe, store_b, panel * kPanelRows, KB,
-                                                       sq + (size_t)b * dq, lane)
-                         : warp_confirm_identical(maybe, a.panels + (size_t)panel * panel_stride,
-                                                  sq + (size_t)b * dq, dq, lane);
+                // identity (src/metrics.rs:7-19, :148-151): every column of my row matched query b
+                const bool identical = valid && ((maybe_mask >> b) & 1u);
                 u64 key = kKeyMax;
                 if (valid)
                     key = make_key(finish_distance(acc[b], mag_a, mag_b[b], identical), a.row_base + row);
@@ -771,10 +834,12 @@ __global__ void __launch_bounds__(kBulkThreads, 1) scan_topk_bulk_kernel(const B
             parity ^= 1;
         }
     }
+    BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 4);
 #pragma unroll
     for (int b = 0; b < QB; b++) top[b].finish(lane);
     __syncthreads();
-    scan_epilogue<kBulkWarps, QB>(lists, K, a.k, a.cta_keys, a.fin, a.fuse_final != 0);
+    BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 5);
+    scan_epilogue<W, QB>(lists, K, a.k, a.cta_keys, a.fin, a.fuse_final != 0);
 }
 
 // ------------------------------------------------------------------------------------------
