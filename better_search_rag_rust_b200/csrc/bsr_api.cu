@@ -549,6 +549,7 @@ static int launch_scan_bulk_t(bsr_store* s, const ScanArgs& a, unsigned grid, u3
     ba.s = a;
     ba.stages = stages;
     ba.active_warps = active_warps;
+    ba.interleave = getenv("BSR_INTERLEAVE") ? (u32)atoi(getenv("BSR_INTERLEAVE")) : 1u;
     scan_topk_bulk_kernel<QB, BF16, W>
         <<<grid, W * 32, bulk_smem_bytes(s, a.k_pad, stages, QB, active_warps, W), st>>>(ba);
     s->launches++;

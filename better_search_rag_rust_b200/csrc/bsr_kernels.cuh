@@ -589,6 +589,7 @@ struct BulkScanArgs {
     ScanArgs s;
     u32 stages;        // ring depth per warp (>= 2)
     u32 active_warps;  // warps per CTA that own at least one panel (the ring is sized for these)
+    u32 interleave;    // 1: panels dealt round-robin over CTAs first (small stores); 0: over a CTA's warps first
 };
 
 // QB queries share one pass over the store: the row chunk is read from shared memory once and
@@ -620,7 +621,7 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
     // count is not a multiple of the warp count the extra panels spread over all SMs (each SM's
     // share of HBM bandwidth is what bounds it), and a small store uses as many SMs as it has panels
     const u32 total_warps = gridDim.x * W;
-    const u32 panel0 = warp * gridDim.x + blockIdx.x;
+    const u32 panel0 = ba.interleave ? warp * gridDim.x + blockIdx.x : blockIdx.x * W + warp;
     const u32 KB = dq >> 4;                                      // bf16: 64-column blocks
     const u32 cpp = BF16 ? KB : (dq + CH - 1) / CH;              // chunks per 32-row panel
     const u32 my_panels = panel0 < a.n_panels ? (a.n_panels - 1 - panel0) / total_warps + 1 : 0;
@@ -718,7 +719,12 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
                     acc[b] = dot8_seq_bf16(acc[b], v, qa, qb2);
                     if (need_qnorm) qsq[b] = sq4_seq(sq4_seq(qsq[b], qa), qb2);
                 }
-                if (maybe_mask) {  // rare: my row has matched a query on every column so far
+            }
+            if (maybe_mask) {
+                // rare: my row has matched a query on every column so far -- compare this block too
+                // (out of the hot loop: the stage is still in shared memory)
+                for (u32 cc = 0; cc < 8; cc++) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(rp + ((cc ^ sw) << 4));
 #pragma unroll
                     for (int b = 0; b < QB; b++)
                         if (((maybe_mask >> b) & 1u) &&
@@ -784,7 +790,10 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
                         acc[b] = dot4_seq(acc[b], v, q);
                         if (need_qnorm) qsq[b] = sq4_seq(qsq[b], q);
                     }
-                    if (maybe_mask) {
+                }
+                if (maybe_mask) {  // rare; out of the hot loop, the stage is still in shared memory
+                    for (int u = 0; u < CH; u++) {
+                        const float4 v = sp[u * 32];
 #pragma unroll
                         for (int b = 0; b < QB; b++)
                             if (((maybe_mask >> b) & 1u) && differs4(v, sq[b * dq + j0 + u])) maybe_mask &= ~(1u << b);
