@@ -765,8 +765,12 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
     const bool bulk = (scan_variant() == 1 || is_bf16(s)) && bulk_stages(s, K, 1) >= 2;
     CHECK(bulk || !is_bf16(s), BSR_ERR_UNSUPPORTED, "search: BF16 stores need the bulk-async scan kernel");
     // bulk kernel: one CTA per SM, or one per panel when the store has fewer panels than SMs
-    const unsigned grid = bulk ? std::max(1u, std::min<unsigned>((unsigned)s->n_sm, n_panels))
-                               : scan_grid(s, n_panels, kScanWarps);
+    // BSR_MAX_GRID: test hook -- fewer CTAs give every warp many panels, which is what exercises the
+    // steady-state (post-fill) top-k insertion on stores small enough for the CPU oracle
+    unsigned grid_cap = (unsigned)s->n_sm;
+    if (const char* e = getenv("BSR_MAX_GRID")) grid_cap = std::max(1u, std::min<unsigned>(grid_cap, (unsigned)atoi(e)));
+    const unsigned grid = bulk ? std::max(1u, std::min<unsigned>(grid_cap, n_panels))
+                               : std::min<unsigned>(grid_cap, scan_grid(s, n_panels, kScanWarps));
     // small stores (more than one, at most four rounds of panels at 8 warps per CTA): 16 warps per CTA
     const u32 per_cta = (n_panels + grid - 1) / grid;
     const bool wide = bulk && per_cta > (u32)kBulkWarps && per_cta <= 4u * kBulkWarps &&

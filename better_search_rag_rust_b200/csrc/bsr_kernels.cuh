@@ -221,13 +221,53 @@ __device__ __forceinline__ void warp_sort_list(u64* list, u32 K, int lane) {
     }
 }
 
+// ---- register-resident 32-key blocks (lane i holds the i-th key) ---------------------------
+// ascending bitonic sort of 32 keys, one per lane
+__device__ __forceinline__ u64 warp_sort32(u64 v, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int d = size >> 1; d >= 1; d >>= 1) {
+            const u64 p = __shfl_xor_sync(0xFFFFFFFFu, v, d);
+            const bool asc = (lane & size) == 0;          // size == 32: every lane ascending
+            const bool keep_min = ((lane & d) == 0) == asc;
+            v = (keep_min == (v < p)) ? v : p;
+        }
+    }
+    return v;
+}
+// a, c: ascending 32-key blocks.  Returns the 32 smallest of the 64 (ascending) and leaves the 32
+// largest (ascending) in c.
+__device__ __forceinline__ u64 warp_merge_split32(u64 a, u64& c, int lane) {
+    const u64 rev = __shfl_sync(0xFFFFFFFFu, c, 31 - lane);
+    u64 lo = a < rev ? a : rev, hi = a < rev ? rev : a;  // both bitonic
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const u64 pl = __shfl_xor_sync(0xFFFFFFFFu, lo, d);
+        const u64 ph = __shfl_xor_sync(0xFFFFFFFFu, hi, d);
+        const bool keep_min = (lane & d) == 0;
+        lo = (keep_min == (lo < pl)) ? lo : pl;
+        hi = (keep_min == (hi < ph)) ? hi : ph;
+    }
+    c = hi;
+    return lo;
+}
+
 // Per-warp running top-k.  Fill phase: the first K keys are appended unsorted and sorted once;
-// after that only keys below the current k-th best (tau) are inserted.
+// after that only keys below the current k-th best (tau) are taken.
+//   K == 32 (k <= 32): a taken key is inserted at once (rare: ~k ln(rows/k) per warp).
+//   K  > 32: taken keys collect in a register block (one per lane); when 32 are pending the block
+//   is sorted with shuffles and rippled through the list's 32-key blocks (merge-split: the block
+//   keeps the smaller half, the larger half carries on), skipping the blocks that lie entirely
+//   below it.  ~K/64 shuffle merges per 32 candidates instead of a ~K/64-step shared-memory
+//   shift per candidate (k = 1024 on a 12.5 M-row shard: 2.7 ms of inserts per scan before).
 struct WarpTopK {
     u64* list;
     int k;
     u32 K, cnt;
     u64 tau;
+    u64 pend;  // K > 32: my pending candidate (lanes < pc)
+    u32 pc;    // K > 32: number of pending candidates (warp-uniform)
 
     __device__ __forceinline__ void init(u64* l, u32 k_, u32 K_, int lane) {
         list = l;
@@ -235,8 +275,25 @@ struct WarpTopK {
         K = K_;
         cnt = 0;
         tau = kKeyMax;
+        pend = kKeyMax;
+        pc = 0;
         for (u32 j = lane; j < K; j += 32) list[j] = kKeyMax;
         __syncwarp();
+    }
+    __device__ __forceinline__ void flush(int lane) {
+        u64 carry = warp_sort32((u32)lane < pc ? pend : kKeyMax, lane);
+        for (u32 b = 0; b < K; b += 32) {
+            const u64 cmin = __shfl_sync(0xFFFFFFFFu, carry, 0);
+            if (cmin == kKeyMax) break;  // nothing left to place
+            const u64 a = list[b + lane];
+            const u64 amax = __shfl_sync(0xFFFFFFFFu, a, 31);
+            if (cmin > amax) continue;   // the whole carry belongs above this block
+            list[b + lane] = warp_merge_split32(a, carry, lane);
+        }
+        __syncwarp();
+        tau = list[k - 1];
+        pend = kKeyMax;
+        pc = 0;
     }
     __device__ __forceinline__ void offer(u64 key, int lane) {
         if (cnt < K) {  // warp-uniform
@@ -250,17 +307,32 @@ struct WarpTopK {
             return;
         }
         unsigned m = __ballot_sync(0xFFFFFFFFu, key < tau);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const u64 x = __shfl_sync(0xFFFFFFFFu, key, src);
-            if (x < tau) warp_list_insert(list, k, x, lane, tau);
+        if (K == 32) {
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const u64 x = __shfl_sync(0xFFFFFFFFu, key, src);
+                if (x < tau) warp_list_insert(list, k, x, lane, tau);
+            }
+            return;
         }
+        if (!m) return;
+        const u32 c = (u32)__popc(m);
+        if (pc + c > 32) flush(lane);
+        // lane d in [pc, pc + c) takes the (d - pc)-th candidate of this offer
+        const u32 nth = (u32)lane - pc;
+        const unsigned src = __fns(m, 0, (nth < c ? nth : 0u) + 1);
+        const u64 v = __shfl_sync(0xFFFFFFFFu, key, (int)(src & 31u));
+        if (nth < c) pend = v;
+        pc += c;
+        if (pc == 32) flush(lane);
     }
     __device__ __forceinline__ void finish(int lane) {
         if (cnt < K) {
             __syncwarp();
             warp_sort_list(list, K, lane);
+        } else if (pc) {
+            flush(lane);
         }
     }
 };

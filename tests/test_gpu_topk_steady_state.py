@@ -1,0 +1,57 @@
+"""GPU: the per-warp running top-k *after* its fill phase.
+
+On stores small enough for the CPU oracle a full grid gives every warp at most a few panels, so
+its K-slot list never fills and the steady-state path (threshold test, K == 32: in-place insert,
+K > 32: batched block merge, `WarpTopK::flush`) would go untested.  BSR_MAX_GRID (a test hook read
+by the library on every search) caps the grid so that each warp scans thousands of rows."""
+import os
+
+import numpy as np
+import pytest
+
+import better_search_rag_rust_b200 as bsr
+from oracle import c_oracle as co
+
+pytestmark = pytest.mark.gpu
+SEED = 0x5EED0001
+
+
+def _bits(x):
+    return np.asarray(x, dtype=np.float32).view(np.uint32)
+
+
+@pytest.fixture
+def small_grid(request, monkeypatch):
+    monkeypatch.setenv("BSR_MAX_GRID", str(request.param))
+    yield request.param
+
+
+@pytest.mark.parametrize("small_grid", [1, 3], indirect=True)
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_steady_state_topk_matches_oracle(small_grid, dtype):
+    n = 30000
+    rows = co.generate_rows(SEED, 0, n, 768)
+    # descending quality: later rows are better matches, so every warp keeps inserting
+    q = co.generate_rows(SEED + 3, 0, 1, 768)[0]
+    w = np.linspace(0.0, 0.9, n, dtype=np.float32)[:, None]
+    rows = (rows * (1 - w) + q[None, :] * w).astype(np.float32)
+    st = bsr.GpuVectorstore(None, True, dtype=dtype)
+    st.append_many(rows)
+    st.set_tensor_min_batch(0)
+    eng = bsr.CudaShardEngine(st)
+    ref_rows = co.round_bf16(rows) if dtype == "bf16" else rows
+    for k in (10, 33, 50, 100, 300, 1024):
+        for qq in (q, ref_rows[n // 2]):
+            got = bsr.compute_local_top_k(None, 0, 1, k, qq, engine=eng)
+            wi, wd = co.compute_local_top_k(ref_rows, 0, 1, k, qq)
+            assert [p[0] for p in got] == wi.tolist(), (k,)
+            assert _bits([p[1] for p in got]).tolist() == _bits(wd).tolist(), (k,)
+    # batches share the pass; every query keeps its own list
+    qs = np.concatenate([q[None, :], co.generate_rows(SEED + 5, 0, 4, 768)])
+    for k in (50, 200):
+        idx, dist, cnt = eng.local_top_k(qs, k)
+        for i in range(len(qs)):
+            wi, wd = co.compute_local_top_k(ref_rows, 0, 1, k, qs[i])
+            assert idx[i, : cnt[i]].tolist() == wi.tolist(), (k, i)
+            assert _bits(dist[i, : cnt[i]]).tolist() == _bits(wd).tolist(), (k, i)
+    st.close()
