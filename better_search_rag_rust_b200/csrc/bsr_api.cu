@@ -782,8 +782,9 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
           "search: dim %u with top_k %u needs %zu bytes of shared memory (limit %zu)", s->dim, k,
           smem, s->smem_optin);
     TRY(ensure(s->cta_keys, (size_t)nq * grid * K * sizeof(u64)));
-    // k <= 32: the scan's last CTA merges the per-CTA lists and unpacks -> one kernel per launch
-    const bool fuse = (K == 32);
+    // k <= 128: the scan's last CTA merges the per-CTA lists and unpacks -> one kernel per launch
+    // (the reference's own k is 50, src/main.rs:110).  BSR_NO_FUSE_WIDE=1: k > 32 through the merge tree.
+    const bool fuse = (K == 32) || (K <= 128 && !getenv("BSR_NO_FUSE_WIDE"));
     if (!s->d_counter.p) {
         TRY(ensure(s->d_counter, 256));
         CU(cudaMemsetAsync(s->d_counter.p, 0, 256, st));

@@ -414,6 +414,50 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 #define BSR_STAMP(dbg, cond, slot) do { } while (0)
 #endif
 
+// Last-CTA fold for 32 < K <= 128 (NB = K/32 register blocks per lane): this warp's running best K
+// keys live in `best[NB]` (ascending blocks).  A list's first block is fetched with all the other
+// lists' (one L2 round trip); its later blocks are fetched only while the list can still
+// contribute (its previous block's largest key is below the running K-th best), which on data in
+// no particular order is almost never.
+template <int NB>
+__device__ __forceinline__ void fold_block(u64 (&best)[NB], u64 in, int lane) {
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        const u64 cmin = __shfl_sync(0xFFFFFFFFu, in, 0);
+        const u64 bmax = __shfl_sync(0xFFFFFFFFu, best[j], 31);
+        if (cmin < bmax) best[j] = warp_merge_split32(best[j], in, lane);  // else: all of `in` lies above block j
+    }
+}
+template <int NB, int W>
+__device__ __forceinline__ void fold_cta_lists(const u64* src, u32 n_lists, u64 (&best)[NB], int warp, int lane) {
+    constexpr u32 K = NB * 32;
+    constexpr u32 B = 10;  // lists per batch: their first two blocks are fetched together (one L2 round trip)
+    for (u32 l0 = warp; l0 < n_lists; l0 += B * W) {
+        u64 t0[B], t1[B];
+#pragma unroll
+        for (u32 i = 0; i < B; i++) {
+            const u32 l = l0 + i * W;
+            t0[i] = l < n_lists ? ldcg_u64(src + (size_t)l * K + lane) : kKeyMax;
+            t1[i] = l < n_lists ? ldcg_u64(src + (size_t)l * K + 32 + lane) : kKeyMax;
+        }
+#pragma unroll
+        for (u32 i = 0; i < B; i++) {
+            const u32 l = l0 + i * W;
+            if (l >= n_lists) break;  // warp-uniform
+            u64 in = t0[i];
+            for (int b = 0;; b++) {
+                const u64 in_max = __shfl_sync(0xFFFFFFFFu, in, 31);
+                fold_block<NB>(best, in, lane);
+                const u64 kth = __shfl_sync(0xFFFFFFFFu, best[NB - 1], 31);
+                // the list is ascending: once a block's largest key is not below the running K-th
+                // best, nothing after it can enter
+                if (b + 1 == NB || !(in_max < kth)) break;
+                in = (b == 0) ? t1[i] : ldcg_u64(src + (size_t)l * K + (size_t)(b + 1) * 32 + lane);
+            }
+        }
+    }
+}
+
 // End of a scan CTA that handled NQ queries: for each query reduce the W per-warp lists
 // (lists[q][w][K] in shared memory) to the CTA's best K and publish them to
 // cta_keys[q][cta][K]; when the launch fuses the final stage (K == 32) the last CTA to finish
@@ -450,6 +494,51 @@ __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta
     if (!s_is_last) return;
     BSR_STAMP(fo.dbg, tid == 0, 8);
     __threadfence();
+    if (K != 32) {
+        // 32 < K <= 128: per query every warp folds its share of the CTA lists into K/32 register
+        // blocks; the W partial results meet in shared memory and are reduced like the per-warp lists
+        for (int q = 0; q < NQ; q++) {
+            const u64* src = cta_keys + q * q_stride;
+            u64* mine = lists + ((size_t)q * W + warp) * K;
+            if (K == 64) {
+                u64 best[2] = {kKeyMax, kKeyMax};
+                fold_cta_lists<2, W>(src, gridDim.x, best, warp, lane);
+                mine[lane] = best[0];
+                mine[32 + lane] = best[1];
+            } else {
+                u64 best[4] = {kKeyMax, kKeyMax, kKeyMax, kKeyMax};
+                fold_cta_lists<4, W>(src, gridDim.x, best, warp, lane);
+#pragma unroll
+                for (int j = 0; j < 4; j++) mine[j * 32 + lane] = best[j];
+            }
+        }
+        __syncthreads();
+        for (int q = 0; q < NQ; q++) {
+            u64* ql = lists + (size_t)q * W * K;
+            cta_merge_lists(ql, W, K);  // ends with __syncthreads()
+            u32 valid = 0;
+            for (u32 j = tid; j < K; j += W * 32) {
+                const u64 v = ql[j];
+                fo.keys[(size_t)q * K + j] = v;
+                if (fo.idx && j < k) {
+                    const bool ok = v != kKeyMax;
+                    fo.idx[(size_t)q * k + j] = ok ? (v & 0xFFFFFFFFull) : 0ull;
+                    fo.dist[(size_t)q * k + j] = ok ? __uint_as_float(bits_from_ordered((u32)(v >> 32))) : 0.0f;
+                    valid += ok ? 1u : 0u;
+                }
+            }
+            if (fo.idx) {  // K <= 128 <= blockDim.x: at most one key per thread; warps 0-3 hold them all
+                const u32 wsum = __reduce_add_sync(0xFFFFFFFFu, valid);
+                __shared__ u32 s_valid[4];
+                if (warp < 4 && lane == 0) s_valid[warp] = wsum;
+                __syncthreads();
+                if (tid == 0) fo.count[q] = s_valid[0] + s_valid[1] + s_valid[2] + s_valid[3];
+                __syncthreads();
+            }
+        }
+        if (tid == 0) *fo.done_counter = 0;
+        return;
+    }
     // K == 32: every warp folds a strided subset of the CTA lists in registers, per query
     for (int q = 0; q < NQ; q++) {
         u64 v = kKeyMax;
@@ -506,7 +595,7 @@ struct ScanArgs {
     u64* cta_keys;         // [gridDim.x][k_pad]
     u32 n_rows, n_panels, dq, dim, k, k_pad;
     u32 row_base;          // global index of local row 0
-    u32 fuse_final;        // 1: the last CTA also merges all CTA lists (requires k_pad == 32)
+    u32 fuse_final;        // 1: the last CTA also merges all CTA lists and unpacks (requires k_pad <= 128)
     FinalOut fin;
     unsigned long long* dbg;  // debug builds (-DBSR_TC_TIMELINE): globaltimer stamps, else unused
 };

@@ -527,32 +527,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
         const u32 lane_addr = ((u32)(warp * 32) << 16);
         float qsq = 0.0f;
         const bool vec_ok = (a.dim % 4 == 0) && ((reinterpret_cast<size_t>(qp) & 15) == 0);
-        for (u32 cb = 0; cb < KB * 2; cb++) {  // 32 elements -> 16 packed columns per store
-            float f[32];
-            if (vec_ok && active && cb * 32 + 32 <= a.dim) {
-                const float4* q4 = reinterpret_cast<const float4*>(qp + cb * 32);
+        // Every lane reads its own query row (3 KiB at a 3 KiB stride), so this loop is bound by L2
+        // round trips: four 32-element blocks are fetched (32 independent 128-bit loads) before the
+        // first is converted -- tcgen05.st is an asm volatile the compiler will not move loads across.
+        // bf16 rounding: cvt.rn.bf16x2.f32 (RNE; same values as f32_to_bf16_rne for every non-NaN input).
+        const u32 n_cb = KB * 2;  // 32 elements -> 16 packed columns per store
+        for (u32 cb0 = 0; cb0 < n_cb; cb0 += 4) {
+            float f[4][32];
 #pragma unroll
-                for (int e = 0; e < 8; e++) {
-                    const float4 t4 = q4[e];
-                    f[4 * e] = t4.x; f[4 * e + 1] = t4.y; f[4 * e + 2] = t4.z; f[4 * e + 3] = t4.w;
-                }
-            } else {
+            for (u32 u = 0; u < 4; u++) {
+                const u32 cb = cb0 + u;
+                if (cb < n_cb) {
+                    if (vec_ok && active && cb * 32 + 32 <= a.dim) {
+                        const float4* q4 = reinterpret_cast<const float4*>(qp + cb * 32);
 #pragma unroll
-                for (int e = 0; e < 32; e++) {
-                    const u32 c = cb * 32 + e;
-                    f[e] = (active && c < a.dim) ? qp[c] : 0.0f;
+                        for (int e = 0; e < 8; e++) {
+                            const float4 t4 = q4[e];
+                            f[u][4 * e] = t4.x; f[u][4 * e + 1] = t4.y; f[u][4 * e + 2] = t4.z; f[u][4 * e + 3] = t4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; e++) {
+                            const u32 c = cb * 32 + e;
+                            f[u][e] = (active && c < a.dim) ? qp[c] : 0.0f;
+                        }
+                    }
                 }
             }
-            u32 r[16];
 #pragma unroll
-            for (int e = 0; e < 16; e++) {
-                const unsigned short lo = f32_to_bf16_rne(f[2 * e]), hi = f32_to_bf16_rne(f[2 * e + 1]);
-                const float flo = __uint_as_float((u32)lo << 16), fhi = __uint_as_float((u32)hi << 16);
-                qsq = __fadd_rn(qsq, __fmul_rn(flo, flo));  // |b| over the rounded query, sequential
-                qsq = __fadd_rn(qsq, __fmul_rn(fhi, fhi));
-                r[e] = (u32)lo | ((u32)hi << 16);
+            for (u32 u = 0; u < 4; u++) {
+                const u32 cb = cb0 + u;
+                if (cb < n_cb) {
+                    u32 r[16];
+#pragma unroll
+                    for (int e = 0; e < 16; e++) {
+                        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r[e]) : "f"(f[u][2 * e + 1]), "f"(f[u][2 * e]));
+                        const float flo = bf16_lo(r[e]), fhi = bf16_hi(r[e]);
+                        qsq = __fadd_rn(qsq, __fmul_rn(flo, flo));  // |b| over the rounded query, sequential
+                        qsq = __fadd_rn(qsq, __fmul_rn(fhi, fhi));
+                    }
+                    tmem_st16(tmem_a + lane_addr + cb * 16, r);
+                }
             }
-            tmem_st16(tmem_a + lane_addr + cb * 16, r);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();

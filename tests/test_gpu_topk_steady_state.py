@@ -55,3 +55,31 @@ def test_steady_state_topk_matches_oracle(small_grid, dtype):
             assert idx[i, : cnt[i]].tolist() == wi.tolist(), (k, i)
             assert _bits(dist[i, : cnt[i]]).tolist() == _bits(wd).tolist(), (k, i)
     st.close()
+
+
+@pytest.mark.parametrize("small_grid", [3, 148], indirect=True)
+def test_fused_final_merge_when_one_cta_holds_the_whole_top_k(small_grid):
+    """k <= 128: the last CTA folds every CTA's list, fetching a list's later 32-key blocks only
+    while it can still contribute.  Here the best 128 rows sit in panels 0, 3, 6 and 9, which a
+    grid of 3 CTAs deals to CTA 0 alone, so its list supplies all four blocks."""
+    n = 2000
+    rows = co.generate_rows(SEED, 0, n, 768)
+    q = co.generate_rows(SEED + 3, 0, 1, 768)[0]
+    rng = np.random.default_rng(5)
+    for p in (0, 3, 6, 9):
+        for r in range(32):
+            rows[p * 32 + r] = q + rng.uniform(-0.05, 0.05, 768).astype(np.float32)
+    st = bsr.GpuVectorstore(None, True)
+    st.append_many(rows)
+    eng = bsr.CudaShardEngine(st)
+    for k in (33, 50, 64, 100, 128):
+        got = bsr.compute_local_top_k(None, 0, 1, k, q, engine=eng)
+        wi, wd = co.compute_local_top_k(rows, 0, 1, k, q)
+        assert [p[0] for p in got] == wi.tolist(), (k,)
+        assert _bits([p[1] for p in got]).tolist() == _bits(wd).tolist(), (k,)
+    qs = np.stack([q, rows[7], co.generate_rows(SEED + 5, 0, 1, 768)[0]])
+    idx, dist, cnt = eng.local_top_k(qs, 50)
+    for i in range(len(qs)):
+        wi, wd = co.compute_local_top_k(rows, 0, 1, 50, qs[i])
+        assert idx[i, : cnt[i]].tolist() == wi.tolist() and _bits(dist[i, : cnt[i]]).tolist() == _bits(wd).tolist()
+    st.close()
