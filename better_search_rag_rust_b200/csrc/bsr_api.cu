@@ -114,6 +114,9 @@ static int ensure(DevBuf& b, size_t bytes) {
     return BSR_OK;
 }
 
+// results up to this size are written by the kernels directly into pinned host memory (bsr_search)
+constexpr size_t kDirectResultBytes = 4096;
+
 static int ensure_pinned(bsr_store* s, size_t bytes) {
     if (s->h_pinned_bytes >= bytes) return BSR_OK;
     if (s->h_pinned) CU(cudaFreeHost(s->h_pinned));
@@ -913,6 +916,13 @@ extern "C" int bsr_merge_device(bsr_store* s, const uint64_t* d_lists, uint32_t 
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
     const u32 K = bsr_candidate_slots(k);
+    if (K == 32 && n_lists <= 4096) {  // one warp per query folds the lists in registers
+        merge32_kernel<<<nq, 32, 0, st>>>((const u64*)d_lists, n_lists, (size_t)nq * K, K, k, (u64*)d_out, nullptr,
+                                          nullptr, nullptr);
+        s->launches++;
+        CU(cudaGetLastError());
+        return BSR_OK;
+    }
     const u32 max_per_cta = std::max<u32>(2, kMergeMaxKeys / K);
     const size_t inter = (size_t)nq * ((n_lists + max_per_cta - 1) / max_per_cta) * K * sizeof(u64);
     TRY(ensure(s->merge_a, inter));
@@ -960,10 +970,14 @@ extern "C" int bsr_search(bsr_store* s, const float* queries, uint32_t nq, uint3
         return BSR_OK;
     }
     CU(cudaMemcpyAsync(s->d_queries.p, h, qbytes, cudaMemcpyHostToDevice, s->stream));
-    char* r = (char*)s->d_result.p;
+    // Small results (a few queries): the kernel that unpacks writes them straight into the pinned
+    // host block (mapped into the device's address space under UVA) -- the D2H transfer still
+    // happens every call, as posted PCIe writes instead of a separate copy operation.
+    const bool direct = rbytes <= kDirectResultBytes;
+    char* r = direct ? h + off_r : (char*)s->d_result.p;
     TRY(search_device_impl(s, (const float*)s->d_queries.p, nq, k, (u64*)s->d_cand.p, (u64*)r,
                            (float*)(r + ibytes), (u32*)(r + ibytes + dbytes), s->stream));
-    CU(cudaMemcpyAsync(h + off_r, r, rbytes, cudaMemcpyDeviceToHost, s->stream));
+    if (!direct) CU(cudaMemcpyAsync(h + off_r, r, rbytes, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     memcpy(out_idx, h + off_r, ibytes);
     memcpy(out_dist, h + off_r + ibytes, dbytes);
@@ -1156,13 +1170,22 @@ extern "C" int bsr_search_parallel(bsr_store* s, bsr_comm* c, const float* queri
         const size_t inter = (size_t)nq * ((c->n_ranks + max_per_cta - 1) / max_per_cta) * K * sizeof(u64);
         TRY(ensure(s->merge_a, inter));
         TRY(ensure(s->merge_b, inter));
-        TRY(merge_tree(s, (const u64*)s->d_gather.p, (u32)c->n_ranks, nq, K, (size_t)nq * K, K, merged, s->stream));
-        char* r = (char*)s->d_result.p;
-        unpack_kernel<<<nq, 128, 0, s->stream>>>(merged, K, k, (u64*)r, (float*)(r + ibytes),
-                                                 (u32*)(r + ibytes + dbytes));
+        const bool direct = rbytes <= kDirectResultBytes;  // see bsr_search
+        char* r = direct ? h + off_r : (char*)s->d_result.p;
+        if (K == 32) {  // merge + unpack in one launch, one warp per query
+            merge32_kernel<<<nq, 32, 0, s->stream>>>((const u64*)s->d_gather.p, (u32)c->n_ranks, (size_t)nq * K, K, k,
+                                                     nullptr, (u64*)r, (float*)(r + ibytes),
+                                                     (u32*)(r + ibytes + dbytes));
+        } else {
+            TRY(merge_tree(s, (const u64*)s->d_gather.p, (u32)c->n_ranks, nq, K, (size_t)nq * K, K, merged,
+                           s->stream));
+            unpack_kernel<<<nq, 128, 0, s->stream>>>(merged, K, k, (u64*)r, (float*)(r + ibytes),
+                                                     (u32*)(r + ibytes + dbytes));
+            s->launches++;
+        }
         s->launches++;
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(h + off_r, r, rbytes, cudaMemcpyDeviceToHost, s->stream));
+        if (!direct) CU(cudaMemcpyAsync(h + off_r, r, rbytes, cudaMemcpyDeviceToHost, s->stream));
     }
     CU(cudaStreamSynchronize(s->stream));
     if (root) {

@@ -1066,6 +1066,40 @@ __global__ void pack_sort_lists_kernel(const u64* __restrict__ idx, const float*
     for (u32 j = threadIdx.x; j < K; j += blockDim.x) lists[base + j] = buf[j];
 }
 
+// K3 for 32-slot lists (k <= 32), e.g. the cross-rank merge after the all-gather: one warp per
+// query folds all lists in registers (lane i holds a list's i-th key) and, when asked, unpacks the
+// result in the same launch.  list l of query q starts at in + l*list_stride + q*query_stride.
+__global__ void __launch_bounds__(32) merge32_kernel(const u64* __restrict__ in, u32 n_lists, size_t list_stride,
+                                                     size_t query_stride, u32 k, u64* __restrict__ out_keys,
+                                                     u64* __restrict__ idx, float* __restrict__ dist,
+                                                     u32* __restrict__ count) {
+    const u32 q = blockIdx.x;
+    const int lane = threadIdx.x;
+    const u64* src = in + (size_t)q * query_stride;
+    u64 v = kKeyMax;
+    for (u32 l0 = 0; l0 < n_lists; l0 += 16) {
+        u64 t[16];
+#pragma unroll
+        for (u32 i = 0; i < 16; i++) t[i] = (l0 + i < n_lists) ? src[(size_t)(l0 + i) * list_stride + lane] : kKeyMax;
+#pragma unroll
+        for (u32 i = 0; i < 16; i++) {
+            const u64 their_best = __shfl_sync(0xFFFFFFFFu, t[i], 0);
+            const u64 my_worst = __shfl_sync(0xFFFFFFFFu, v, 31);
+            if (their_best < my_worst) v = warp_merge32(v, t[i], lane);
+        }
+    }
+    if (out_keys) out_keys[(size_t)q * 32 + lane] = v;
+    if (idx) {
+        const bool ok = (u32)lane < k && v != kKeyMax;
+        if ((u32)lane < k) {
+            idx[(size_t)q * k + lane] = ok ? (v & 0xFFFFFFFFull) : 0ull;
+            dist[(size_t)q * k + lane] = ok ? __uint_as_float(bits_from_ordered((u32)(v >> 32))) : 0.0f;
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+        if (lane == 0) count[q] = (u32)__popc(m);
+    }
+}
+
 // candidates[q][K] -> idx[q][k] (u64, as the reference's usize), dist[q][k], count[q]
 __global__ void unpack_kernel(const u64* __restrict__ cand, u32 K, u32 k, u64* __restrict__ idx,
                               float* __restrict__ dist, u32* __restrict__ count) {

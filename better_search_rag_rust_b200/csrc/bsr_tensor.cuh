@@ -277,10 +277,9 @@ __device__ __noinline__ bool row_equals_query_bf16(const unsigned char* tiles, u
 __device__ __forceinline__ u64 pack_survivor(u32 row, float score) {
     return ((u64)row << 32) | (u64)__float_as_uint(score);
 }
-__device__ __forceinline__ u64 survivor_key(const TensorScanArgs& a, u64 raw, const float* qp, float mag_b) {
+__device__ __forceinline__ u64 survivor_key(const TensorScanArgs& a, u64 raw, float na, const float* qp, float mag_b) {
     const u32 row = (u32)(raw >> 32);
     const float score = __uint_as_float((u32)raw);
-    const float na = __ldg(a.norms + row);
     float dist = 1.0f;  // zero magnitude (src/metrics.rs:157-159)
     // identity (src/metrics.rs:148-151) precedes every other rule; within 1e-10 per element implies
     // sim ~ 1 unless the query is tiny (|b| < 1e-6), in which case every survivor is checked
@@ -299,7 +298,7 @@ __device__ __forceinline__ u64 survivor_key(const TensorScanArgs& a, u64 raw, co
 __device__ __noinline__ u64 compact_survivors(const TensorScanArgs& a, u64* buf, u32 n, const float* qp,
                                               float mag_b, u64* keys_tmp) {
     const u32 k = a.k;
-    for (u32 i = 0; i < n; i++) keys_tmp[i] = survivor_key(a, buf[i], qp, mag_b);
+    for (u32 i = 0; i < n; i++) keys_tmp[i] = survivor_key(a, buf[i], __ldg(a.norms + (u32)(buf[i] >> 32)), qp, mag_b);
     for (u32 x = 0; x < k; x++) {  // selection of the k smallest keys, entries move with their keys
         u32 best = x;
         for (u32 y = x + 1; y < n; y++)
@@ -752,7 +751,27 @@ __global__ void __launch_bounds__(256) finalize_survivors_kernel(const TensorSca
     const u64* src = a.survivors + (size_t)list * (2 * kTcSurvivorCap);
     const float* qp = a.queries + (size_t)q * a.dim;
     const float mag_b = a.q_mag[q];
-    for (u32 j = lane; j < P; j += 32) scratch[j] = j < n ? survivor_key(a, src[j], qp, mag_b) : kKeyMax;
+    // eight survivors per lane at a time: their records and then their rows' norms (random 4-byte
+    // reads, DRAM latency) are all in flight before the first key is computed
+    for (u32 j0 = 0; j0 < P; j0 += 256) {
+        u64 raw[8];
+        float na[8];
+#pragma unroll
+        for (u32 u = 0; u < 8; u++) {
+            const u32 j = j0 + u * 32 + lane;
+            raw[u] = j < n ? src[j] : 0ull;
+        }
+#pragma unroll
+        for (u32 u = 0; u < 8; u++) {
+            const u32 j = j0 + u * 32 + lane;
+            na[u] = j < n ? __ldg(a.norms + (u32)(raw[u] >> 32)) : 0.0f;
+        }
+#pragma unroll
+        for (u32 u = 0; u < 8; u++) {
+            const u32 j = j0 + u * 32 + lane;
+            if (j < P) scratch[j] = j < n ? survivor_key(a, raw[u], na[u], qp, mag_b) : kKeyMax;
+        }
+    }
     __syncwarp();
     warp_sort_list(scratch, P, lane);
     u64* out = a.cta_keys + (size_t)list * K;
