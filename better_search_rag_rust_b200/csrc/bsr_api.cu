@@ -726,6 +726,19 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
             CU(cudaGetLastError());
         }
         TRY(prof_end(s, st));
+        if (getenv("BSR_TC_STATS") && q0 == 0) {  // debug: survivors per (query, cluster) list
+            std::vector<u32> h((size_t)QS * n_clusters);
+            CU(cudaStreamSynchronize(st));
+            CU(cudaMemcpy(h.data(), a.surv_count, h.size() * sizeof(u32), cudaMemcpyDeviceToHost));
+            unsigned long long sum = 0;
+            u32 mx = 0;
+            const size_t cnt = (size_t)a.nq_valid * n_clusters;
+            for (size_t i = 0; i < cnt; i++) {
+                sum += h[i];
+                mx = std::max(mx, h[i]);
+            }
+            fprintf(stderr, "tensor stats: %zu lists, survivors mean %.1f max %u\n", cnt, (double)sum / cnt, mx);
+        }
 #ifdef BSR_TC_TIMELINE
         if (tl_on) {  // debug only: dump the pipeline stamps of CTAs 0 and 1 (cycles since CTA 0's first stamp)
             std::vector<long long> h(2 * kTlTiles * 8);

@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
         u64* surv_buf = a.survivors + ((size_t)q * n_clusters + cluster_id) * (2 * kTcSurvivorCap);
         u32 surv_cnt = 0;
         float thr = -INFINITY;    // prune rows with t < thr, t = S / |a|
-        u32 next_refresh = max(learn, 1u);  // refresh the bound after this many tiles of the sequence
+        u32 next_refresh = max(learn >> 1, 1u);  // refresh the bound after this many tiles of the sequence
 
         for (u32 sq = 0; sq < n_seq; sq++) {
             const u32 buf = sq & 1;
@@ -689,7 +689,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
                 // Merge my class maxima with everyone else's and refresh the bound.  The bound improves
                 // like log(rows seen), so the refresh points are spaced geometrically (x 1.5).  Branch-free:
                 // 64 coalesced L2 reads per class group, a predicated RED.MAX per improved class.
-                next_refresh = max(next_refresh + 1, next_refresh + (next_refresh >> 1));
+                // First points: learn/2 (publish early, so that nobody finds an unpublished class -- an
+                // unpublished class means "no bound", i.e. every row survives -- when it reads at
+                // `learn`), learn, learn + 1 (picks up what the others published at `learn`).
+                next_refresh = next_refresh < learn ? learn
+                                                    : max(next_refresh + 1, next_refresh + (next_refresh >> 1) - (next_refresh == learn ? (next_refresh >> 1) : 0u));
                 if (active && !tiny_q) {
                     float bound = INFINITY;
                     for (u32 c0 = 0; c0 < kc; c0 += kTcN) {  // one 64-class group at a time
