@@ -766,7 +766,9 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BSR_STAMP(a.dbg, blockIdx.x == 0 && threadIdx.x == 0, 0);
     const u32 dq = a.dq, S = ba.stages, K = a.k_pad;
-    // [ring: active_warps*S*4KiB | queries: QB*dq*16 | lists: QB*W*K*8 | mbarriers: W*S*8]
+    // [ring: active_warps*S*4KiB | queries: dq*QB*16, sq[j*QB + b] = column-quad j of query b (one
+    //  address register per quad, the query index is an immediate offset) | lists: QB*W*K*8 |
+    //  mbarriers: W*S*8]
     unsigned char* ring_all = smem_raw;
     float4* sq = reinterpret_cast<float4*>(ring_all + (size_t)ba.active_warps * S * kChunkBytes);
     u64* lists = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(sq) + (size_t)QB * dq * 16);
@@ -828,7 +830,7 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
         v.y = (c + 1 < a.dim) ? qp[c + 1] : 0.0f;
         v.z = (c + 2 < a.dim) ? qp[c + 2] : 0.0f;
         v.w = (c + 3 < a.dim) ? qp[c + 3] : 0.0f;
-        sq[t] = v;
+        sq[(size_t)j * QB + b] = v;  // interleaved by query: column-quad j of all QB queries is contiguous
     }
     WarpTopK top[QB];
 #pragma unroll
@@ -869,14 +871,14 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
                 maybe_mask = 0;
 #pragma unroll
                 for (int b = 0; b < QB; b++)
-                    maybe_mask |= differs8_bf16(v0, sq[b * dq], sq[b * dq + 1]) ? 0u : (1u << b);
+                    maybe_mask |= differs8_bf16(v0, sq[b], sq[(1) * QB + b]) ? 0u : (1u << b);
             }
 #pragma unroll 4
             for (u32 cc = 0; cc < 8; cc++) {
                 const uint4 v = *reinterpret_cast<const uint4*>(rp + ((cc ^ sw) << 4));
 #pragma unroll
                 for (int b = 0; b < QB; b++) {
-                    const float4 qa = sq[b * dq + q0i + 2 * cc], qb2 = sq[b * dq + q0i + 2 * cc + 1];
+                    const float4 qa = sq[(q0i + 2 * cc) * QB + b], qb2 = sq[(q0i + 2 * cc + 1) * QB + b];
                     acc[b] = dot8_seq_bf16(acc[b], v, qa, qb2);
                     if (need_qnorm) qsq[b] = sq4_seq(sq4_seq(qsq[b], qa), qb2);
                 }
@@ -889,7 +891,7 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
 #pragma unroll
                     for (int b = 0; b < QB; b++)
                         if (((maybe_mask >> b) & 1u) &&
-                            differs8_bf16(v, sq[b * dq + q0i + 2 * cc], sq[b * dq + q0i + 2 * cc + 1]))
+                            differs8_bf16(v, sq[(q0i + 2 * cc) * QB + b], sq[(q0i + 2 * cc + 1) * QB + b]))
                             maybe_mask &= ~(1u << b);
                 }
             }
@@ -904,14 +906,14 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
                 if (ci == 0) {
                     maybe_mask = 0;
 #pragma unroll
-                    for (int b = 0; b < QB; b++) maybe_mask |= differs4(v[0], sq[b * dq]) ? 0u : (1u << b);
+                    for (int b = 0; b < QB; b++) maybe_mask |= differs4(v[0], sq[b]) ? 0u : (1u << b);
                 }
                 if (need_qnorm) {  // first panel: the |b| chain runs interleaved with the dot chain
 #pragma unroll
                     for (int u = 0; u < CH; u++) {
 #pragma unroll
                         for (int b = 0; b < QB; b++) {
-                            const float4 q = sq[b * dq + j0 + u];
+                            const float4 q = sq[(j0 + u) * QB + b];
                             acc[b] = dot4_seq(acc[b], v[u], q);
                             qsq[b] = sq4_seq(qsq[b], q);
                         }
@@ -920,7 +922,7 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
 #pragma unroll
                     for (int u = 0; u < CH; u++) {
 #pragma unroll
-                        for (int b = 0; b < QB; b++) acc[b] = dot4_seq(acc[b], v[u], sq[b * dq + j0 + u]);
+                        for (int b = 0; b < QB; b++) acc[b] = dot4_seq(acc[b], v[u], sq[(j0 + u) * QB + b]);
                     }
                 }
                 if (maybe_mask) {  // rare: my row has matched a query on every column so far
@@ -929,7 +931,7 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
                         if ((maybe_mask >> b) & 1u) {
                             bool d = false;
 #pragma unroll
-                            for (int u = 0; u < CH; u++) d |= differs4(v[u], sq[b * dq + j0 + u]);
+                            for (int u = 0; u < CH; u++) d |= differs4(v[u], sq[(j0 + u) * QB + b]);
                             if (d) maybe_mask &= ~(1u << b);
                         }
                     }
@@ -940,14 +942,14 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
                     const float4 v0 = sp[0];
                     maybe_mask = 0;
 #pragma unroll
-                    for (int b = 0; b < QB; b++) maybe_mask |= differs4(v0, sq[b * dq]) ? 0u : (1u << b);
+                    for (int b = 0; b < QB; b++) maybe_mask |= differs4(v0, sq[b]) ? 0u : (1u << b);
                 }
 #pragma unroll 2
                 for (int u = 0; u < CH; u++) {
                     const float4 v = sp[u * 32];
 #pragma unroll
                     for (int b = 0; b < QB; b++) {
-                        const float4 q = sq[b * dq + j0 + u];
+                        const float4 q = sq[(j0 + u) * QB + b];
                         acc[b] = dot4_seq(acc[b], v, q);
                         if (need_qnorm) qsq[b] = sq4_seq(qsq[b], q);
                     }
@@ -957,7 +959,7 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
                         const float4 v = sp[u * 32];
 #pragma unroll
                         for (int b = 0; b < QB; b++)
-                            if (((maybe_mask >> b) & 1u) && differs4(v, sq[b * dq + j0 + u])) maybe_mask &= ~(1u << b);
+                            if (((maybe_mask >> b) & 1u) && differs4(v, sq[(j0 + u) * QB + b])) maybe_mask &= ~(1u << b);
                     }
                 }
             } else {
@@ -967,11 +969,11 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
                     for (int b = 0; b < QB; b++) {
                         if (ci == 0 && u == 0) {
                             if (b == 0) maybe_mask = 0;
-                            maybe_mask |= differs4(v, sq[b * dq]) ? 0u : (1u << b);
+                            maybe_mask |= differs4(v, sq[b]) ? 0u : (1u << b);
                         }
-                        acc[b] = dot4_seq(acc[b], v, sq[b * dq + j0 + u]);
-                        if (need_qnorm) qsq[b] = sq4_seq(qsq[b], sq[b * dq + j0 + u]);
-                        if (((maybe_mask >> b) & 1u) && differs4(v, sq[b * dq + j0 + u])) maybe_mask &= ~(1u << b);
+                        acc[b] = dot4_seq(acc[b], v, sq[(j0 + u) * QB + b]);
+                        if (need_qnorm) qsq[b] = sq4_seq(qsq[b], sq[(j0 + u) * QB + b]);
+                        if (((maybe_mask >> b) & 1u) && differs4(v, sq[(j0 + u) * QB + b])) maybe_mask &= ~(1u << b);
                     }
                 }
             }
