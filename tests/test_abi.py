@@ -36,6 +36,20 @@ def test_python_binding_covers_the_header():
         assert getattr(L, name) is not None
 
 
+def test_rust_and_cxx_bindings_cover_the_header():
+    """The Rust crate (source only: no cargo in this image) and the C++ host mirror must bind the
+    same entry points as the header, so that they cannot drift apart unnoticed."""
+    declared = set(_declared())
+    rust = open(os.path.join(ROOT, "rust", "src", "lib.rs")).read()
+    rust_fns = set(re.findall(r"pub fn (bsr_[a-z0-9_]+)\s*\(", rust))
+    assert rust_fns == declared, sorted(rust_fns ^ declared)
+    hpp = open(os.path.join(ROOT, "better_search_rag_rust_b200", "csrc", "bsr_host.hpp")).read()
+    used = set(re.findall(r"\b(bsr_[a-z0-9_]+)\s*\(", hpp))
+    assert used <= declared | {"bsr_check"}, sorted(used - declared)
+    # the search path proper is reachable from C++
+    assert {"bsr_store_create", "bsr_store_append", "bsr_search", "bsr_search_parallel"} <= used
+
+
 def test_header_compiles_as_c_and_cxx(tmp_path):
     for comp, ext, std in (("gcc", "c", "-std=c99"), ("g++", "cpp", "-std=c++17")):
         f = tmp_path / f"t.{ext}"

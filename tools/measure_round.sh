@@ -1,3 +1,6 @@
+# Round measurement pass on one B200 (run under gpurun): GPU tests, bench.py (+ reference arm), ncu launch
+# lists and --set full captures (exported as CSV pages; the .ncu-rep files stay in /tmp), every single-GPU
+# BASELINE config, and the tensor-kernel pipeline timelines.  Outputs land in gpurun_out/.
 set -x
 timeout -s KILL 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
 timeout -s KILL 400 python bench.py > gpurun_out/r01_bench_n1.json 2> gpurun_out/r01_bench_n1.err; tail -c 300 gpurun_out/r01_bench_n1.json
