@@ -664,7 +664,9 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
     u32 mode = (nq > kTcQ && s->n_sm >= 2) ? 2u : 0u;  // measured: pairs (2) beat multicast (1) by ~6 %
     if (const char* e = getenv("BSR_TENSOR_MODE")) mode = (u32)std::min(2, std::max(0, atoi(e)));
     const u32 C = mode == 0 ? 1u : 2u;
-    const unsigned n_clusters = std::max(1u, std::min<unsigned>((unsigned)s->n_sm / C, n_tiles));
+    unsigned n_clusters = std::max(1u, std::min<unsigned>((unsigned)s->n_sm / C, n_tiles));
+    // BSR_MAX_GRID: test hook (see search_device_impl) -- few clusters make every survivor list long
+    if (const char* e = getenv("BSR_MAX_GRID")) n_clusters = std::max(1u, std::min<unsigned>(n_clusters, (unsigned)atoi(e) / C));
     const unsigned grid = n_clusters * C;
     const u32 QS = C * kTcQ;  // queries per launch
     const u32 stages = tensor_stages(s, mode), stage_kb = tensor_stage_kb(mode);

@@ -185,8 +185,8 @@ BSR_API int bsr_search_parallel(bsr_store *shard, bsr_comm *comm, const float *q
 
 /* BF16 stores only: query batches of at least `min_batch` queries (default 32) are scanned on the
  * tensor cores (tcgen05, queries in tensor memory).  That path is not bit-exact: the tensor core
- * accumulates the (exact) bf16 products in a different order, so distances agree with the exact
- * path to ~1e-6.  0 disables it: every search then uses the exact scan.  Needs dim <= 768 and
+ * accumulates the (exact) bf16 products in a different order and truncates, so distances agree
+ * with the exact path to 2e-6 (4e-6 for rows nearly parallel to the query).  0 disables it: every search then uses the exact scan.  Needs dim <= 768 and
  * top_k <= 128; other shapes always use the exact scan. */
 BSR_API int bsr_store_set_tensor_min_batch(bsr_store *store, uint32_t min_batch);
 
