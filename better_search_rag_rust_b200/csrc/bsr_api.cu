@@ -15,6 +15,14 @@
 #include "bsr_kernels.cuh"
 #include "bsr_tensor.cuh"
 
+// the scan kernels are compiled in bsr_inst.cu (one translation unit per group, in parallel)
+namespace bsr {
+#define BSR_INST(...) extern template __global__ __VA_ARGS__;
+#include "bsr_instances.inc"
+#undef BSR_INST
+}  // namespace bsr
+
+
 using namespace bsr;
 
 // ---------------------------------------------------------------------------------------------

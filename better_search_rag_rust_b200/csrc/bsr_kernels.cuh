@@ -1014,6 +1014,7 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
     scan_epilogue<W, QB>(lists, K, a.k, a.cta_keys, a.fin, a.fuse_final != 0);
 }
 
+#ifndef BSR_TEMPLATES_ONLY  // the plain (non-template) kernels are compiled once, in bsr_api.cu
 // ------------------------------------------------------------------------------------------
 // K3: merge candidate lists (cross-CTA after the scan; cross-rank after the all-gather).
 //     restates compute_global_top_k's sort + first-k (src/mpi_helpers/metrics.rs:147-170).
@@ -1277,5 +1278,7 @@ __global__ void synth_rows_bf16_kernel(uint4* __restrict__ tiles, u32 row_lo, u3
     for (int e = 0; e < 8; e++) v[e] = (col + e < dim) ? synth_elem(rk, col + e) : 0.0f;
     tiles[(size_t)(row_lo >> 6) * KB * 512 + t] = pack8_bf16(v);
 }
+
+#endif  // BSR_TEMPLATES_ONLY
 
 }  // namespace bsr

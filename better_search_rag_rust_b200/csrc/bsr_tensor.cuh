@@ -739,6 +739,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
     }
 }
 
+#ifndef BSR_TEMPLATES_ONLY
 // One warp per (query, CTA) survivor list: raw (row, score) pairs -> exact keys (the reference's
 // distance formula) -> bitonic sort -> the best k_pad written as an ascending candidate list.
 __global__ void __launch_bounds__(256) finalize_survivors_kernel(const TensorScanArgs a, u32 n_cta) {
@@ -781,5 +782,7 @@ __global__ void __launch_bounds__(256) finalize_survivors_kernel(const TensorSca
     u64* out = a.cta_keys + (size_t)list * K;
     for (u32 j = lane; j < K; j += 32) out[j] = scratch[j];
 }
+
+#endif  // BSR_TEMPLATES_ONLY
 
 }  // namespace bsr
