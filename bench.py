@@ -4,13 +4,19 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): 1 M x 768 fp32 rows resident in each GPU's HBM, one query,
-exact top-10 cosine distance.  One step = one query.  At N > 1 every rank holds its own 1 M-row
-shard (weak scaling: the store is N x 1 M rows, row-sharded as
-src/mpi_helpers/load_balance.rs:24-42 would), a step is scan -> NCCL all-gather of the k candidate
-slots -> on-device merge on root.  `value` counts 1 M-row shard scans per second (= queries/s x N,
-the whole-job aggregate the contract asks for; at N = 1 it is plain queries/s); the queries/s
-against the whole N x 1 M-row store is reported beside it as `queries_per_s_whole_store`.
+Workload (BASELINE.json configs[3], the north-star target, one shard of it per GPU): 12.5 M x 768 fp32
+rows resident in each GPU's HBM (38.4 GB), one query, exact top-10 cosine distance.  At N = 8 the
+store is the full 100 M x 768 rows, row-sharded as src/mpi_helpers/load_balance.rs:24-42 would.  One
+step = one query against the whole N-shard store: scan of every shard -> exchange of the k candidate
+slots -> on-device merge on root (weak scaling: rows per GPU fixed).
+
+`value` counts 12.5 M-row shard scans per second (= queries/s x N: the whole-job aggregate the
+contract asks for, proportional to rows scanned per second; at N = 1 it is plain queries/s).  The
+queries/s against the whole N-shard store is reported beside it as `queries_per_s_whole_store`.
+`extra_1m` repeats the measurement on BASELINE.json configs[1] (1 M x 768 per GPU).
+
+After the timed regions every rank checks its shard's COMPLETE top-k against the CPU oracle run
+block-wise over the regenerated rows, and root checks the merged list (`parity_checked`).
 
 `--impl reference` times the reference's own CPU path (the C restatement in oracle/, since the
 Rust reference cannot be built here) on the host cores; see DESIGN.md.
@@ -32,36 +38,44 @@ sys.path.insert(0, HERE)
 DIM = 768
 TOP_K = 10
 SEED = 0x5EED0001
-ROWS_PER_GPU = 1_000_000
-METRIC = "queries/sec (exact top-10 cosine, 768-d fp32)"
-UNIT = "queries/s"
+ROWS_PER_GPU = 12_500_000      # 100 M rows / 8 GPUs (BASELINE.json configs[3]); 38.4 GB of fp32 per GPU
+ROWS_EXTRA = 1_000_000         # BASELINE.json configs[1]
+METRIC = "shard-queries/sec: queries/sec x row shards scanned per query (exact top-10 cosine, 768-d fp32)"
+UNIT = "shard-queries/s"
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--rows-per-gpu", type=int, default=ROWS_PER_GPU)
     ap.add_argument("--top-k", type=int, default=TOP_K)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run oracle check (profiling runs)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the 1 M-row extra measurement")
+    ap.add_argument("--exchange", choices=["auto", "nccl"], default="auto",
+                    help="cross-rank candidate exchange of the e2e leg: library default, or ncclAllGather only")
     return ap.parse_args()
 
 
 def workload_config(n_gpus: int, rows_per_gpu: int, top_k: int) -> dict:
+    which = ("BASELINE.json configs[3] shard: 100 M x 768 over 8 GPUs" if rows_per_gpu == ROWS_PER_GPU
+             else "BASELINE.json configs[1]" if rows_per_gpu == ROWS_EXTRA else "custom size")
     return {
         "workload": f"{rows_per_gpu} x {DIM} fp32 rows per GPU, HBM-resident, single query, "
-                    f"exact top-{top_k} cosine (BASELINE.json configs[1] shard)",
+                    f"exact top-{top_k} cosine ({which})",
         "rows_per_gpu": rows_per_gpu,
         "rows_total": rows_per_gpu * n_gpus,
         "dim": DIM,
         "top_k": top_k,
         "queries_per_step": 1,
         "sharding": f"row blocks over {n_gpus} GPU(s), one process per GPU" +
-                    (", NCCL all-gather of k candidate slots + on-device merge" if n_gpus > 1 else ""),
-        "value_counts": "shard scans per second = queries/s x n_gpus (one query scans every shard)",
-        "l2": "inputs larger than L2 (3.07 GB streamed per step per GPU vs 126 MB L2); no flush needed",
+                    (", exchange of k candidate slots + on-device merge on root" if n_gpus > 1 else ""),
+        "value_counts": "row shards scanned per second = queries/s x n_gpus (one query scans every shard); "
+                        "queries/s against the whole store is queries_per_s_whole_store",
+        "l2": f"inputs larger than L2 ({rows_per_gpu * DIM * 4 / 1e9:.2f} GB streamed per step per GPU vs 126 MB L2); no flush needed",
         "query": "row 0 of the store (the reference's self-query, src/main.rs:111,120)",
     }
 
@@ -208,7 +222,8 @@ def run_reference(args):
     sec_probe = cpu_rate(probe, threads, args.top_k, 2)
     rows_per_s = 65_536 / sec_probe
     budget = 100.0
-    sample_rows = int(min(args.rows_per_gpu, max(4096, rows_per_s * budget / max(1, steps + warmup))))
+    # at most 2 M rows (6 GB of host memory) per step: the rate is flat in the row count
+    sample_rows = int(min(args.rows_per_gpu, 2_000_000, max(4096, rows_per_s * budget / max(1, steps + warmup))))
     rows = probe if sample_rows <= 65_536 else _generate_host_rows(sample_rows, threads)
     rows = rows[:sample_rows]
     q = rows[0].copy()
@@ -218,7 +233,7 @@ def run_reference(args):
     for _ in range(steps):
         co.parallel_top_k_similarity_search(rows, threads, args.top_k, q, n_threads=threads)
     dt = time.perf_counter() - t0
-    # one step scanned sample_rows rows; a whole 1 M-row shard scan takes rows_per_gpu/sample_rows steps
+    # one step scanned sample_rows rows; a whole shard scan takes rows_per_gpu/sample_rows steps
     value = (steps / dt) * (sample_rows / args.rows_per_gpu)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -250,16 +265,27 @@ def _peak_gbs() -> tuple[float, str]:
 
 
 def _traffic_per_launch(rows_per_gpu: int):
-    """dram bytes per scan launch from the committed ncu capture, if it matches this workload."""
-    p = os.path.join(HERE, "profiles", "r01_scan_summary.json")
+    """dram bytes per scan launch.  DRAM counters cannot be read inside a timed run; the figure comes
+    from the committed ncu capture of this same command (profiles/r02_scan_summary.json) when its
+    row count matches, and the line says so in `traffic_source`."""
+    p = os.path.join(HERE, "profiles", "r02_scan_summary.json")
     try:
         with open(p) as f:
             j = json.load(f)
-        if int(j.get("rows")) == rows_per_gpu:
-            return float(j["dram_bytes_read"]) + float(j["dram_bytes_write"])
+        for cap in j.get("captures", []):
+            if int(cap.get("rows")) == rows_per_gpu and cap.get("dtype", "f32") == "f32":
+                return (float(cap["dram_bytes_read"]) + float(cap["dram_bytes_write"]),
+                        f"profiles/r02_scan_summary.json ({cap.get('source', 'ncu --set full')})")
     except Exception:
         pass
-    return None
+    return None, "no committed ncu capture for this row count"
+
+
+def oracle_shard_top_k(rank: int, n: int, k: int, q: np.ndarray, threads: int):
+    """The reference's compute_local_top_k (src/mpi_helpers/metrics.rs:36-50) for generator rows
+    [rank*n, (rank+1)*n), run block-wise on `threads` host threads -> (global idx, dist)."""
+    from oracle import c_oracle as co
+    return co.scan_generated_parallel(SEED, rank * n, n, k, q, threads=threads, dim=DIM)
 
 
 def run_b200(args):
@@ -282,45 +308,14 @@ def run_b200(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    n, k, steps, warmup = args.rows_per_gpu, args.top_k, args.steps, max(3, args.warmup)
-
-    store = bsr.GpuVectorstore(None, True, device=local, row_base=rank * n, dim=DIM, capacity_rows=n)
-    store.append_synthetic(SEED, rank * n, n)  # global store = generator rows [0, world*n)
-    eng = bsr.CudaShardEngine(store)
-    slots = bsr.candidate_slots(k)
-
-    # the query: row 0 of the global store (lives on rank 0), broadcast like src/main.rs:123-125
-    q_host = torch.zeros((1, DIM), dtype=torch.float32).pin_memory()
-    if rank == 0:
-        q_host.copy_(torch.from_numpy(store.get(0)).reshape(1, -1))
-    q_dev = q_host.to(dev)
-    if world > 1:
-        dist.broadcast(q_dev, src=0)
-        q_host.copy_(q_dev.cpu())
-    q_np = q_host.numpy()
-
-    cand = torch.empty((1, slots), dtype=torch.int64, device=dev)
-    gathered = torch.empty((world, 1, slots), dtype=torch.int64, device=dev)
-    merged = torch.empty((1, slots), dtype=torch.int64, device=dev)
-
-    def step_device():
-        eng.search_candidates(q_dev, k, out=cand)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, cand)
-            if rank == 0:
-                eng.merge(gathered, k, out=merged)
+    k, steps, warmup = args.top_k, args.steps, max(3, args.warmup)
 
     comm = None
     if world > 1:
-        # the library's own NCCL communicator: the id travels over the host channel (here torch's)
+        # the library's own communicator: the id travels over the host channel (here torch's)
         ids = [bsr.BsrComm.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         comm = bsr.BsrComm(ids[0], world, rank, local)
-
-    def step_e2e():
-        if world == 1:
-            return eng.local_top_k(q_np, k)  # bsr_search: host buffers in, host buffers out
-        return comm.search(eng, q_np, k)     # bsr_search_parallel: one C-ABI call per rank
 
     def fence():
         torch.cuda.synchronize()
@@ -328,55 +323,128 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def max_over_ranks(x: float) -> float:
+    def reduce_ranks(x: float, op) -> float:
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
     sampler = ClockSampler(local)
     sampler.start()
 
-    # ---- device-resident region: `value` and the roofline ------------------------------------
-    for _ in range(warmup):
-        step_device()
-    fence()
-    store.set_profiling(True)
-    launches0 = store.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.perf_counter()
-    e0.record()
-    for _ in range(steps):
-        step_device()
-    e1.record()
-    fence()
-    t_wall1 = time.perf_counter()
-    ms_dev = max_over_ranks(e0.elapsed_time(e1))
-    launches = sum_over_ranks(store.launch_count() - launches0)
-    scan_ms, n_scans = store.scan_profile()
-    store.set_profiling(False)
+    def measure(n: int, n_steps: int, check: bool) -> dict:
+        """Both timed regions (device-resident and end to end) on an n-row shard per GPU, then the
+        parity check of the complete top-k against the oracle."""
+        store = bsr.GpuVectorstore(None, True, device=local, row_base=rank * n, dim=DIM, capacity_rows=n)
+        store.append_synthetic(SEED, rank * n, n)  # global store = generator rows [0, world*n)
+        if args.exchange == "nccl":
+            store.set_option("no_mailbox", 1)
+        eng = bsr.CudaShardEngine(store)
+        slots = bsr.candidate_slots(k)
 
-    # ---- end-to-end region: host query in, host top-k out, every step ----------------------------
-    for _ in range(warmup):
-        step_e2e()
-    fence()
-    t0 = time.perf_counter()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    for _ in range(steps):
-        res = step_e2e()
-    g1.record()
-    fence()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+        # the query: row 0 of the global store (lives on rank 0), broadcast like src/main.rs:123-125
+        q_host = torch.zeros((1, DIM), dtype=torch.float32).pin_memory()
+        if rank == 0:
+            q_host.copy_(torch.from_numpy(store.get(0)).reshape(1, -1))
+        q_dev = q_host.to(dev)
+        if world > 1:
+            dist.broadcast(q_dev, src=0)
+            q_host.copy_(q_dev.cpu())
+        q_np = q_host.numpy()
+
+        cand = torch.empty((1, slots), dtype=torch.int64, device=dev)
+        gathered = torch.empty((world, 1, slots), dtype=torch.int64, device=dev)
+        merged = torch.empty((1, slots), dtype=torch.int64, device=dev)
+
+        def step_device():
+            eng.search_candidates(q_dev, k, out=cand)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, cand)
+                if rank == 0:
+                    eng.merge(gathered, k, out=merged)
+
+        def step_e2e():
+            if world == 1:
+                return eng.local_top_k(q_np, k)  # bsr_search: host buffers in, host buffers out
+            return comm.search(eng, q_np, k)     # bsr_search_parallel: one C-ABI call per rank
+
+        # ---- device-resident region: `value` and the roofline --------------------------------
+        for _ in range(warmup):
+            step_device()
+        fence()
+        store.set_profiling(True)
+        launches0 = store.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall0 = time.perf_counter()
+        e0.record()
+        for _ in range(n_steps):
+            step_device()
+        e1.record()
+        fence()
+        t_wall1 = time.perf_counter()
+        ms_dev = reduce_ranks(e0.elapsed_time(e1), dist.ReduceOp.MAX if world > 1 else None)
+        launches = reduce_ranks(store.launch_count() - launches0, dist.ReduceOp.SUM if world > 1 else None)
+        scan_ms, n_scans = store.scan_profile()
+        store.set_profiling(False)
+
+        # ---- end-to-end region: host query in, host top-k out, every step ------------------------
+        for _ in range(warmup):
+            step_e2e()
+        fence()
+        t0 = time.perf_counter()
+        for _ in range(n_steps):
+            res = step_e2e()
+        fence()
+        e2e_s = reduce_ranks(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
+
+        out = {"n": n, "steps": n_steps, "ms_dev": ms_dev, "launches": launches, "scan_ms": scan_ms,
+               "n_scans": n_scans, "e2e_s": e2e_s, "scan_bytes": store.scan_bytes(),
+               "t_wall": (t_wall0, t_wall1), "parity": "skipped (--no-parity)"}
+
+        # ---- parity: the COMPLETE top-k against the oracle, outside the timed regions -----------
+        if check:
+            threads = max(1, _host_threads() // world)
+            t_chk = time.perf_counter()
+            li, ld, lc = eng.local_top_k(q_np, k)                      # this shard, through bsr_search
+            wi, wd = oracle_shard_top_k(rank, n, k, q_np[0], threads)  # compute_local_top_k on the same rows
+            ok_local = (int(lc[0]) == len(wi) and li[0, :lc[0]].tolist() == wi.tolist()
+                        and ld[0, :lc[0]].view(np.uint32).tolist() == wd.view(np.uint32).tolist())
+            lists = [(wi, wd)]
+            if world > 1:
+                lists = [None] * world if rank == 0 else None
+                dist.gather_object((wi, wd), lists, dst=0)
+            ok_global = True
+            if rank == 0:
+                from oracle import c_oracle as co
+                gi = np.concatenate([p[0] for p in lists])             # rank order (metrics.rs:86-89)
+                gd = np.concatenate([p[1] for p in lists])
+                fi, fd = co.compute_global_top_k(gi, gd, k)            # metrics.rs:141-171
+                idx, dst, cnt = res
+                ok_global = (int(cnt[0]) == len(fi) and idx[0, :cnt[0]].tolist() == fi.tolist()
+                             and dst[0, :cnt[0]].view(np.uint32).tolist() == fd.view(np.uint32).tolist()
+                             # the self-query comes back first with distance exactly 0 (src/main.rs:148-154)
+                             and int(idx[0, 0]) == 0 and float(dst[0, 0]) == 0.0)
+            n_bad = reduce_ranks(0.0 if (ok_local and ok_global) else 1.0, dist.ReduceOp.SUM if world > 1 else None)
+            if n_bad:
+                raise SystemExit(f"PARITY FAILURE on {int(n_bad)} rank(s): GPU top-{k} differs from the oracle "
+                                 f"(rank {rank}: local ok={ok_local}, merged ok={ok_global})")
+            out["parity"] = "full"
+            out["parity_detail"] = (
+                f"every rank: its shard's complete top-{k} (bsr_search) == oracle compute_local_top_k over the "
+                f"{n} regenerated rows, indices and distance bits; root: merged list of the e2e leg == oracle "
+                f"compute_global_top_k of the rank-ordered oracle lists; {threads} host thread(s) per rank, "
+                f"{time.perf_counter() - t_chk:.1f} s")
+        store.close()
+        return out
+
+    main = measure(args.rows_per_gpu, steps, not args.no_parity)
+    extra = None
+    if not args.no_extra and args.rows_per_gpu != ROWS_EXTRA:
+        extra = measure(ROWS_EXTRA, max(steps, 200), not args.no_parity)
     sampler.stop()
+    if comm is not None:
+        comm.close()
 
     if rank != 0:
         if world > 1:
@@ -384,46 +452,57 @@ def run_b200(args):
             dist.destroy_process_group()
         return None
 
-    # sanity: the self-query must come back first with distance exactly 0 (src/main.rs:148-154)
-    idx, dst, cnt = res
-    assert int(idx[0, 0]) == 0 and float(dst[0, 0]) == 0.0 and int(cnt[0]) == k, (idx, dst, cnt)
-
     peak, peak_src = _peak_gbs()
-    scan_bytes = store.scan_bytes()
-    avg_scan_ms = scan_ms / max(1, n_scans)
-    achieved = scan_bytes / (avg_scan_ms * 1e-3) / 1e9
-    q_per_s = steps / (ms_dev * 1e-3)
+
+    def summarize(m: dict) -> dict:
+        avg_scan_ms = m["scan_ms"] / max(1, m["n_scans"])
+        q_per_s = m["steps"] / (m["ms_dev"] * 1e-3)
+        achieved = m["scan_bytes"] / (avg_scan_ms * 1e-3) / 1e9
+        traffic, traffic_src = _traffic_per_launch(m["n"])
+        return {
+            "value": q_per_s * world, "queries_per_s_whole_store": q_per_s,
+            "ms_per_step": m["ms_dev"] / m["steps"],
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "scan_topk_bulk_kernel<1,false,8> (fused cosine scan + top-k), rank 0",
+                "algorithmic_bytes_per_launch": m["scan_bytes"],
+                "avg_launch_ms": avg_scan_ms, "launches_timed": m["n_scans"],
+                "kernel_share_of_step": avg_scan_ms / (m["ms_dev"] / m["steps"]),
+                "peak_source": peak_src,
+                "frac_of_nominal_8TBs": achieved / 8000.0,
+            },
+            "e2e": {"value": m["steps"] / m["e2e_s"] * world, "unit": UNIT,
+                    "queries_per_s_whole_store": m["steps"] / m["e2e_s"],
+                    "h2d_bytes_per_step": DIM * 4 * world,
+                    "d2h_bytes_per_step": k * 12 + 4,
+                    "ms_per_step": m["e2e_s"] / m["steps"] * 1e3,
+                    "path": "bsr_search (C ABI, host buffers)" if world == 1 else
+                            "bsr_search_parallel (C ABI, host buffers: scan -> candidate exchange -> merge on root)"},
+            "gpu_launches": int(m["launches"]),
+            "parity_checked": m["parity"], "parity_detail": m.get("parity_detail"),
+        }
+
+    sm = summarize(main)
     line = {
-        "metric": METRIC, "value": q_per_s * world, "unit": UNIT, "n_gpus": world, "steps": steps,
-        "warmup": warmup, "ms_per_step": ms_dev / steps, "higher_is_better": True,
+        "metric": METRIC, "value": sm["value"], "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": sm["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(world, n, k),
-        "queries_per_s_whole_store": q_per_s,
-        "wall_ms_per_step": (t_wall1 - t_wall0) / steps * 1e3,
-        "roofline": {
-            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": _traffic_per_launch(n),
-            "kernel": "scan_topk_f32 (fused cosine scan + top-k), rank 0",
-            "algorithmic_bytes_per_launch": scan_bytes,
-            "avg_launch_ms": avg_scan_ms, "launches_timed": n_scans,
-            "kernel_share_of_step": avg_scan_ms / (ms_dev / steps),
-            "peak_source": peak_src,
-            "frac_of_nominal_8TBs": achieved / 8000.0,
-        },
-        "e2e": {"value": steps / e2e_s * world, "unit": UNIT,
-                "h2d_bytes_per_step": DIM * 4 * world,
-                "d2h_bytes_per_step": k * 12 + 4,
-                "ms_per_step": e2e_s / steps * 1e3,
-                "path": "bsr_search (C ABI, host buffers)" if world == 1 else
-                        "bsr_search_parallel (C ABI, host buffers: scan -> ncclAllGather -> merge on root)"},
-        "gpu_launches": int(launches),
-        "clocks": sampler.summary(t_wall0, t_wall1),
+        "config": workload_config(world, args.rows_per_gpu, k),
+        "queries_per_s_whole_store": sm["queries_per_s_whole_store"],
+        "wall_ms_per_step": (main["t_wall"][1] - main["t_wall"][0]) / steps * 1e3,
+        "roofline": sm["roofline"], "e2e": sm["e2e"], "gpu_launches": sm["gpu_launches"],
+        "parity_checked": sm["parity_checked"], "parity_detail": sm["parity_detail"],
+        "clocks": sampler.summary(*main["t_wall"]),
     }
+    if extra is not None:
+        se = summarize(extra)
+        line["extra_1m"] = {"config": workload_config(world, ROWS_EXTRA, k), "steps": extra["steps"], **se}
     if world == 1 and not args.no_cpu_baseline:
         try:
             from oracle import c_oracle as co
             co.build()
-            line["cpu_baseline"] = cpu_baseline(n, k)
+            line["cpu_baseline"] = cpu_baseline(args.rows_per_gpu, k)
         except Exception as e:  # the GPU numbers stand even if the host leg cannot run
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": _host_threads(),
                                     "kind": "port", "sample": f"failed: {e!r}"}

@@ -8,8 +8,9 @@ vectorstore / search interface.  There is no CPU fallback.
 """
 from ._lib import BsrError, BSR_MAX_TOP_K, LIB_PATH  # noqa: F401
 from .load_balance import RankInterval, RankSlice, interval_by_rank, slice_by_rank  # noqa: F401
-from .metrics import (calculate_accuracy_metrics, format_accuracy_metrics,  # noqa: F401
-                      format_top_k_results, print_top_k_results)
+from .metrics import (agreement_report, calculate_accuracy_metrics, format_accuracy_metrics,  # noqa: F401
+                      format_top_k_results, mean_reciprocal_rank, print_top_k_results, recall_at_k,
+                      result_vectors, top_k_overlap, vectors_are_identical)
 from .search import (ROOT, BsrComm, CudaShardEngine, candidate_slots, compute_global_top_k,  # noqa: F401
                      compute_local_top_k, gather_top_k_results, is_root, open_shard,
                      pack_candidates, parallel_top_k_similarity_search, release_shards,
@@ -17,4 +18,4 @@ from .search import (ROOT, BsrComm, CudaShardEngine, candidate_slots, compute_gl
 from .vectorstore import (GpuVectorstore, NoDataError, SliceArgs, get_global_vstore,  # noqa: F401
                           get_local_vstore)
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -21,6 +21,8 @@ BSR_ERR_UNSUPPORTED = -5
 
 BSR_F32 = 0
 BSR_BF16 = 1
+BSR_COSINE = 0
+BSR_DOT = 1
 BSR_MAX_TOP_K = 1024
 BSR_COMM_ID_BYTES = 128
 
@@ -51,6 +53,8 @@ SIGNATURES = {
     "bsr_store_append": (C.c_int, [_store, C.c_void_p, C.c_uint64]),
     "bsr_store_append_device": (C.c_int, [_store, C.c_void_p, C.c_uint64]),
     "bsr_store_append_synthetic": (C.c_int, [_store, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "bsr_store_set_metric": (C.c_int, [_store, C.c_int]),
+    "bsr_store_metric": (C.c_int, [_store, C.POINTER(C.c_int)]),
     "bsr_store_count": (C.c_int, [_store, _u64p]),
     "bsr_store_dim": (C.c_int, [_store, _u32p]),
     "bsr_store_row_base": (C.c_int, [_store, _u64p]),
@@ -74,6 +78,7 @@ SIGNATURES = {
     "bsr_search_parallel": (C.c_int, [_store, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
     "bsr_store_set_tensor_min_batch": (C.c_int, [_store, C.c_uint32]),
+    "bsr_store_set_option": (C.c_int, [_store, C.c_char_p, C.c_int64]),
     "bsr_store_launch_count": (C.c_int, [_store, _u64p]),
     "bsr_store_last_scan_ms": (C.c_int, [_store, _f32p]),
     "bsr_store_set_profiling": (C.c_int, [_store, C.c_int]),

@@ -59,6 +59,52 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// Ablation switches and test hooks (last section).  Read ONCE, when the library is first
+// used; none is needed in production and every default is the measured optimum.
+// ---------------------------------------------------------------------------------------------
+struct Knobs {
+    int scan_ldg = 0;        // BSR_SCAN_VARIANT=ldg: register-staged scan kernel instead of the bulk-async ring
+    int ldg_u = 0;           // BSR_LDG_U
+    int bulk_stages = 0;     // BSR_BULK_STAGES (0 = default)
+    int max_qb = 8;          // BSR_MAX_QB
+    int no_wide = 0;         // BSR_NO_WIDE
+    int no_fuse_wide = 0;    // BSR_NO_FUSE_WIDE
+    int max_grid = 0;        // BSR_MAX_GRID (test hook, 0 = no cap)
+    int tensor_min_batch = -1;  // BSR_TENSOR_MIN_BATCH
+    int tensor_mode = -1;    // BSR_TENSOR_MODE
+    int tensor_stages = 0;   // BSR_TENSOR_STAGES
+    int tensor_stage_kb = 0; // BSR_TENSOR_STAGE_KB
+    int tc_stats = 0;        // BSR_TC_STATS
+    int no_pdl = 0;          // BSR_NO_PDL: plain stream-ordered launches for back-to-back scans
+    int no_mailbox = 0;      // BSR_NO_MAILBOX: cross-rank exchange through ncclAllGather only
+};
+static const Knobs& knobs() {
+    static const Knobs k = [] {
+        Knobs v;
+        auto geti = [](const char* name, int dflt) {
+            const char* e = getenv(name);
+            return e ? atoi(e) : dflt;
+        };
+        if (const char* e = getenv("BSR_SCAN_VARIANT")) v.scan_ldg = strcmp(e, "ldg") == 0;
+        v.ldg_u = geti("BSR_LDG_U", 0);
+        v.bulk_stages = geti("BSR_BULK_STAGES", 0);
+        v.max_qb = std::max(1, geti("BSR_MAX_QB", 8));
+        v.no_wide = getenv("BSR_NO_WIDE") != nullptr;
+        v.no_fuse_wide = getenv("BSR_NO_FUSE_WIDE") != nullptr;
+        v.max_grid = std::max(0, geti("BSR_MAX_GRID", 0));
+        v.tensor_min_batch = geti("BSR_TENSOR_MIN_BATCH", -1);
+        v.tensor_mode = geti("BSR_TENSOR_MODE", -1);
+        v.tensor_stages = geti("BSR_TENSOR_STAGES", 0);
+        v.tensor_stage_kb = geti("BSR_TENSOR_STAGE_KB", 0);
+        v.tc_stats = getenv("BSR_TC_STATS") != nullptr;
+        v.no_pdl = getenv("BSR_NO_PDL") != nullptr;
+        v.no_mailbox = getenv("BSR_NO_MAILBOX") != nullptr;
+        return v;
+    }();
+    return k;
+}
+
+// ---------------------------------------------------------------------------------------------
 // the store handle
 // ---------------------------------------------------------------------------------------------
 struct DevBuf {
@@ -71,6 +117,8 @@ struct bsr_store {
     u32 dim = 0, dq = 0;  // dq: query quads (f32: ceil(dim/4); bf16: 16 * kb)
     u32 kb = 0;          // bf16 only: 64-column blocks per row
     bsr_dtype dtype = BSR_F32;
+    bsr_metric metric = BSR_COSINE;
+    Knobs kn = knobs();  // environment defaults, overridable per handle with bsr_store_set_option
     u64 row_base = 0;
     u64 n_rows = 0;
     u64 cap_rows = 0;  // multiple of 32
@@ -82,12 +130,19 @@ struct bsr_store {
     size_t smem_optin = 0;
 
     // per-search scratch (grown on demand)
-    DevBuf cta_keys, merge_a, merge_b, d_queries, d_cand, d_result, d_counter, d_gtau, d_surv, d_gather, staging;
+    DevBuf cta_keys, merge_a, merge_b, d_queries, d_cand, d_result, d_counter, d_gtau, d_surv, d_gather, staging, ones;
     u32 tensor_min_batch = 32;  // BF16 stores: batches at least this large use the tcgen05 path (0 = never)
     void* h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
 
     u64 launches = 0;
+    // All calls on a handle share one scratch set (cta_keys, merge buffers, the last-CTA ticket).  The
+    // asynchronous entry points (bsr_search_device / bsr_merge_device / bsr_unpack_device) run on a
+    // caller-supplied stream: each records ev_busy when it has queued its work, and the next call on
+    // ANOTHER stream (the handle's own included) waits on it first, so two calls never overlap.
+    cudaEvent_t ev_busy = nullptr;
+    cudaStream_t busy_stream = nullptr;
+    bool busy = false;
     cudaEvent_t ev_scan0 = nullptr, ev_scan1 = nullptr;
     bool scan_timed = false;
 
@@ -134,6 +189,19 @@ static int ensure_pinned(bsr_store* s, size_t bytes) {
     s->h_pinned_bytes = bytes;
     return BSR_OK;
 }
+
+// see bsr_store::ev_busy
+static int order_after_previous(bsr_store* s, cudaStream_t st) {
+    if (s->busy && s->busy_stream != st) CU(cudaStreamWaitEvent(st, s->ev_busy, 0));
+    return BSR_OK;
+}
+static int mark_busy(bsr_store* s, cudaStream_t st) {
+    CU(cudaEventRecord(s->ev_busy, st));
+    s->busy_stream = st;
+    s->busy = true;
+    return BSR_OK;
+}
+static void mark_idle(bsr_store* s) { s->busy = false; }  // after a host synchronisation of the stream last used
 
 static u32 next_pow2(u32 v) {
     u32 p = 1;
@@ -230,13 +298,14 @@ extern "C" int bsr_store_create(int device, uint32_t dim, bsr_dtype dtype, uint6
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_busy, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev_scan0);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev_scan1);
     if (e != cudaSuccess) {
         delete s;
         return fail(BSR_ERR_CUDA, "bsr_store_create: %s", cudaGetErrorString(e));
     }
-    if (const char* e = getenv("BSR_TENSOR_MIN_BATCH")) s->tensor_min_batch = (u32)std::max(0, atoi(e));
+    if (s->kn.tensor_min_batch >= 0) s->tensor_min_batch = (u32)s->kn.tensor_min_batch;
     s->n_sm = prop.multiProcessorCount;
     s->smem_optin = prop.sharedMemPerBlockOptin;
     if (capacity_rows) {
@@ -253,9 +322,10 @@ extern "C" int bsr_store_create(int device, uint32_t dim, bsr_dtype dtype, uint6
 extern "C" int bsr_store_destroy(bsr_store* s) {
     if (!s) return BSR_OK;
     DeviceGuard g(s->device);
+    if (s->busy) cudaEventSynchronize(s->ev_busy);
     cudaStreamSynchronize(s->stream);
     DevBuf* bufs[] = {&s->cta_keys, &s->merge_a, &s->merge_b, &s->d_queries,
-                      &s->d_cand,   &s->d_result, &s->d_counter, &s->d_gtau, &s->d_surv, &s->d_gather, &s->staging};
+                      &s->d_cand,   &s->d_result, &s->d_counter, &s->d_gtau, &s->d_surv, &s->d_gather, &s->staging, &s->ones};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (s->panels) cudaFree(s->panels);
@@ -263,6 +333,7 @@ extern "C" int bsr_store_destroy(bsr_store* s) {
     if (s->inv_norms) cudaFree(s->inv_norms);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
+    if (s->ev_busy) cudaEventDestroy(s->ev_busy);
     if (s->ev_scan0) cudaEventDestroy(s->ev_scan0);
     if (s->ev_scan1) cudaEventDestroy(s->ev_scan1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -429,6 +500,7 @@ extern "C" int bsr_store_get_many(const bsr_store* cs, uint64_t offset, uint64_t
     DeviceGuard g(s->device);
     const size_t row_bytes = (size_t)s->dim * sizeof(float);
     const u64 chunk_rows = std::max<u64>(1, std::min<u64>(length, (256ull << 20) / row_bytes));
+    TRY(order_after_previous(s, s->stream));
     TRY(ensure(s->staging, (size_t)chunk_rows * row_bytes));
     for (u64 done = 0; done < length; done += chunk_rows) {
         const u64 n = std::min(chunk_rows, length - done);
@@ -507,14 +579,9 @@ static int prof_end(bsr_store* s, cudaStream_t st) {
     return BSR_OK;
 }
 
-static int scan_variant() {
+static int scan_variant(const bsr_store* s) {
     // BSR_SCAN_VARIANT=ldg selects the register-staged kernel (ablation); default: bulk-async ring
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("BSR_SCAN_VARIANT");
-        v = (e && strcmp(e, "ldg") == 0) ? 0 : 1;
-    }
-    return v;
+    return s->kn.scan_ldg ? 0 : 1;
 }
 
 static size_t bulk_smem_bytes(const bsr_store* s, u32 K, u32 stages, u32 qb, u32 active_warps = kBulkWarps,
@@ -531,15 +598,14 @@ static size_t bulk_smem_bytes(const bsr_store* s, u32 K, u32 stages, u32 qb, u32
 static u32 bulk_stages(const bsr_store* s, u32 K, u32 qb, u32 active_warps = kBulkWarps, bool small = false,
                        u32 W = kBulkWarps) {
     u32 st = small ? 24 : 3;
-    if (const char* e = getenv("BSR_BULK_STAGES")) st = std::max(2, atoi(e));
+    if (s->kn.bulk_stages) st = (u32)std::max(2, s->kn.bulk_stages);
     while (st >= 2 && bulk_smem_bytes(s, K, st, qb, active_warps, W) + 1024 > s->smem_optin) st--;
     return st;  // < 2: does not fit
 }
 
 // largest query-batch width (8, 4, 2, 1) whose lists fit next to a >= 2-stage ring
 static u32 bulk_max_qb(const bsr_store* s, u32 K) {
-    u32 cap = 8;
-    if (const char* e = getenv("BSR_MAX_QB")) cap = std::max(1, atoi(e));
+    const u32 cap = (u32)s->kn.max_qb;
     for (u32 qb = 8; qb >= 2; qb >>= 1)
         if (qb <= cap && bulk_stages(s, K, qb) >= 2) return qb;
     return 1;
@@ -560,7 +626,7 @@ static int launch_scan_bulk_t(bsr_store* s, const ScanArgs& a, unsigned grid, u3
     ba.s = a;
     ba.stages = stages;
     ba.active_warps = active_warps;
-    ba.interleave = getenv("BSR_INTERLEAVE") ? (u32)atoi(getenv("BSR_INTERLEAVE")) : 1u;
+    ba.interleave = 1u;  // panels dealt over CTAs first: the ring is sized for active_warps on that assumption
     scan_topk_bulk_kernel<QB, BF16, W>
         <<<grid, W * 32, bulk_smem_bytes(s, a.k_pad, stages, QB, active_warps, W), st>>>(ba);
     s->launches++;
@@ -576,7 +642,7 @@ static int launch_scan_bulk(bsr_store* s, const ScanArgs& a, unsigned grid, u32 
 }
 
 // reduce n_lists lists per query to one; returns the buffer holding [nq][K] in *result
-static int merge_tree(bsr_store* s, const u64* in, u32 n_lists, u32 nq, u32 K, size_t list_stride,
+static int merge_tree(bsr_store* s, const u64* in, u32 n_lists, u32 nq, u32 K, u32 k, size_t list_stride,
                       size_t query_stride, u64* final_out, cudaStream_t st) {
     static thread_local bool configured[64] = {false};
     if (!configured[s->device & 63]) {
@@ -593,7 +659,7 @@ static int merge_tree(bsr_store* s, const u64* in, u32 n_lists, u32 nq, u32 K, s
         const u32 groups = (n_lists + per_cta - 1) / per_cta;
         u64* dst = (groups == 1) ? final_out : ping;
         merge_lists_kernel<<<dim3(groups, nq), kMergeThreads, (size_t)per_cta * K * sizeof(u64), st>>>(
-            cur, n_lists, K, per_cta, list_stride, query_stride, dst);
+            cur, n_lists, K, per_cta, list_stride, query_stride, dst, groups == 1 ? k : K);
         s->launches++;
         CU(cudaGetLastError());
         if (groups == 1) break;
@@ -615,9 +681,9 @@ static unsigned scan_grid(const bsr_store* s, u32 n_panels, int warps_per_cta) {
 // Ring shape (measured on B200, 10 M x 768 bf16, top-100): every stage costs a fixed wait/arm/copy +
 // wait/issue/commit handshake, so stages are large.  Single CTA: 3 x 48 KiB.  Cluster of 2: one
 // whole tile (96 KiB) per stage, 2 stages.  BSR_TENSOR_STAGE_KB / BSR_TENSOR_STAGES override.
-static u32 tensor_stage_kb(u32 mode) {
+static u32 tensor_stage_kb(const bsr_store* s, u32 mode) {
     u32 v = mode == 0 ? kTcStageKB / 2 : kTcStageKB;  // pair mode: 12 half-height blocks = 48 KiB
-    if (const char* e = getenv("BSR_TENSOR_STAGE_KB")) v = (u32)std::min<int>(kTcStageKB, std::max(1, atoi(e)));
+    if (s->kn.tensor_stage_kb) v = (u32)std::min<int>(kTcStageKB, std::max(1, s->kn.tensor_stage_kb));
     return v;
 }
 static size_t tensor_smem_bytes(u32 stage_kb, u32 stages, u32 mode = 0) {
@@ -627,8 +693,8 @@ static size_t tensor_smem_bytes(u32 stage_kb, u32 stages, u32 mode = 0) {
 }
 static u32 tensor_stages(const bsr_store* s, u32 mode) {
     u32 st = mode == 1 ? 2 : 3;
-    if (const char* e = getenv("BSR_TENSOR_STAGES")) st = std::max(2, atoi(e));
-    while (st >= 2 && tensor_smem_bytes(tensor_stage_kb(mode), st, mode) + 2048 > s->smem_optin) st--;
+    if (s->kn.tensor_stages) st = (u32)std::max(2, s->kn.tensor_stages);
+    while (st >= 2 && tensor_smem_bytes(tensor_stage_kb(s, mode), st, mode) + 2048 > s->smem_optin) st--;
     return st;
 }
 static bool tensor_eligible(const bsr_store* s, u32 nq, u32 K) {
@@ -670,14 +736,14 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
     // more than one 128-query group: clusters of 2 CTAs share every store tile (TMA multicast)
     // mode 0: single CTAs; 1: clusters of 2 with multicast tiles; 2: CTA pairs (cta_group::2)
     u32 mode = (nq > kTcQ && s->n_sm >= 2) ? 2u : 0u;  // measured: pairs (2) beat multicast (1) by ~6 %
-    if (const char* e = getenv("BSR_TENSOR_MODE")) mode = (u32)std::min(2, std::max(0, atoi(e)));
+    if (s->kn.tensor_mode >= 0) mode = (u32)std::min(2, s->kn.tensor_mode);
     const u32 C = mode == 0 ? 1u : 2u;
     unsigned n_clusters = std::max(1u, std::min<unsigned>((unsigned)s->n_sm / C, n_tiles));
     // BSR_MAX_GRID: test hook (see search_device_impl) -- few clusters make every survivor list long
-    if (const char* e = getenv("BSR_MAX_GRID")) n_clusters = std::max(1u, std::min<unsigned>(n_clusters, (unsigned)atoi(e) / C));
+    if (s->kn.max_grid) n_clusters = std::max(1u, std::min<unsigned>(n_clusters, (unsigned)s->kn.max_grid / C));
     const unsigned grid = n_clusters * C;
     const u32 QS = C * kTcQ;  // queries per launch
-    const u32 stages = tensor_stages(s, mode), stage_kb = tensor_stage_kb(mode);
+    const u32 stages = tensor_stages(s, mode), stage_kb = tensor_stage_kb(s, mode);
     const size_t smem = tensor_smem_bytes(stage_kb, stages, mode);
     TRY(ensure(s->cta_keys, (size_t)nq * n_clusters * K * sizeof(u64)));
     const size_t gm_bytes = (size_t)QS * ((k + kTcN - 1) / kTcN) * kTcN * sizeof(u32);
@@ -688,6 +754,13 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
     const size_t inter = (size_t)nq * ((n_clusters + max_per_cta - 1) / max_per_cta) * K * sizeof(u64);
     TRY(ensure(s->merge_a, inter));
     TRY(ensure(s->merge_b, inter));
+    if (s->metric == BSR_DOT && !s->ones.p) {
+        TRY(ensure(s->ones, kTcN * sizeof(float)));
+        float h_ones[kTcN];
+        for (u32 i = 0; i < kTcN; i++) h_ones[i] = 1.0f;
+        CU(cudaMemcpyAsync(s->ones.p, h_ones, sizeof h_ones, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));  // h_ones is a stack buffer
+    }
     CU(cudaEventRecord(s->ev_scan0, st));
     for (u32 q0 = 0; q0 < nq; q0 += QS) {
         TensorScanArgs a;
@@ -710,6 +783,12 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
         a.row_base = (u32)s->row_base;
         a.stages = stages;
         a.stage_kb = stage_kb;
+        a.metric = (u32)s->metric;
+        a.norm_stride = kTcN;
+        if (s->metric == BSR_DOT) {  // scores are ranked as they are: a constant block of ones stands in for 1/|a|
+            a.inv_norms = (const float*)s->ones.p;
+            a.norm_stride = 0;
+        }
         a.timeline = nullptr;
         a.tl_start = 0;
 #ifdef BSR_TC_TIMELINE
@@ -736,7 +815,7 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
             CU(cudaGetLastError());
         }
         TRY(prof_end(s, st));
-        if (getenv("BSR_TC_STATS") && q0 == 0) {  // debug: survivors per (query, cluster) list
+        if (s->kn.tc_stats && q0 == 0) {  // debug: survivors per (query, cluster) list
             std::vector<u32> h((size_t)QS * n_clusters);
             CU(cudaStreamSynchronize(st));
             CU(cudaMemcpy(h.data(), a.surv_count, h.size() * sizeof(u32), cudaMemcpyDeviceToHost));
@@ -772,7 +851,7 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
     }
     CU(cudaEventRecord(s->ev_scan1, st));
     s->scan_timed = true;
-    TRY(merge_tree(s, (const u64*)s->cta_keys.p, n_clusters, nq, K, K, (size_t)n_clusters * K, d_cand, st));
+    TRY(merge_tree(s, (const u64*)s->cta_keys.p, n_clusters, nq, K, k, K, (size_t)n_clusters * K, d_cand, st));
     if (d_idx) {
         unpack_kernel<<<nq, 128, 0, st>>>(d_cand, K, k, d_idx, d_dist, d_count);
         s->launches++;
@@ -788,19 +867,19 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
     const u32 K = bsr_candidate_slots(k);
     if (tensor_eligible(s, nq, K)) return search_tensor(s, d_queries, nq, k, d_cand, d_idx, d_dist, d_count, st);
     const u32 n_panels = (u32)((s->n_rows + 31) / 32);
-    const bool bulk = (scan_variant() == 1 || is_bf16(s)) && bulk_stages(s, K, 1) >= 2;
+    const bool bulk = (scan_variant(s) == 1 || is_bf16(s)) && bulk_stages(s, K, 1) >= 2;
     CHECK(bulk || !is_bf16(s), BSR_ERR_UNSUPPORTED, "search: BF16 stores need the bulk-async scan kernel");
     // bulk kernel: one CTA per SM, or one per panel when the store has fewer panels than SMs
     // BSR_MAX_GRID: test hook -- fewer CTAs give every warp many panels, which is what exercises the
     // steady-state (post-fill) top-k insertion on stores small enough for the CPU oracle
     unsigned grid_cap = (unsigned)s->n_sm;
-    if (const char* e = getenv("BSR_MAX_GRID")) grid_cap = std::max(1u, std::min<unsigned>(grid_cap, (unsigned)atoi(e)));
+    if (s->kn.max_grid) grid_cap = std::max(1u, std::min<unsigned>(grid_cap, (unsigned)s->kn.max_grid));
     const unsigned grid = bulk ? std::max(1u, std::min<unsigned>(grid_cap, n_panels))
                                : std::min<unsigned>(grid_cap, scan_grid(s, n_panels, kScanWarps));
     // small stores (more than one, at most four rounds of panels at 8 warps per CTA): 16 warps per CTA
     const u32 per_cta = (n_panels + grid - 1) / grid;
     const bool wide = bulk && per_cta > (u32)kBulkWarps && per_cta <= 4u * kBulkWarps &&
-                      bulk_stages(s, K, 1, std::min<u32>(16, per_cta), true, 16) >= 2 && !getenv("BSR_NO_WIDE");
+                      bulk_stages(s, K, 1, std::min<u32>(16, per_cta), true, 16) >= 2 && !s->kn.no_wide;
     const u32 active_warps = std::min<u32>(wide ? 16u : (u32)kBulkWarps, per_cta);
     const bool small_store = n_panels <= 2u * grid * (wide ? 16u : (u32)kBulkWarps);
     const size_t smem = (size_t)s->dq * sizeof(float4) + (size_t)kScanWarps * K * sizeof(u64);
@@ -810,7 +889,7 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
     TRY(ensure(s->cta_keys, (size_t)nq * grid * K * sizeof(u64)));
     // k <= 128: the scan's last CTA merges the per-CTA lists and unpacks -> one kernel per launch
     // (the reference's own k is 50, src/main.rs:110).  BSR_NO_FUSE_WIDE=1: k > 32 through the merge tree.
-    const bool fuse = (K == 32) || (K <= 128 && !getenv("BSR_NO_FUSE_WIDE"));
+    const bool fuse = (K == 32) || (K <= 128 && !s->kn.no_fuse_wide);
     if (!s->d_counter.p) {
         TRY(ensure(s->d_counter, 256));
         CU(cudaMemsetAsync(s->d_counter.p, 0, 256, st));
@@ -839,6 +918,7 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
         a.k_pad = K;
         a.row_base = (u32)s->row_base;
         a.fuse_final = fuse ? 1u : 0u;
+        a.metric = (u32)s->metric;
         a.fin.done_counter = (u32*)s->d_counter.p;
         a.fin.keys = d_cand + (size_t)q * K;
         a.fin.idx = d_idx ? d_idx + (size_t)q * k : nullptr;
@@ -875,9 +955,9 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
             else if (qb == 4) TRY(launch_scan_bulk<4>(s, a, grid, stages, aw8, st));
             else if (qb == 2) TRY(launch_scan_bulk<2>(s, a, grid, stages, aw8, st));
             else TRY(launch_scan_bulk<1>(s, a, grid, stages, aw8, st));
-        } else if (s->dq % 16 == 0 && getenv("BSR_LDG_U") && atoi(getenv("BSR_LDG_U")) == 16)
+        } else if (s->dq % 16 == 0 && s->kn.ldg_u == 16)
             TRY(launch_scan<16>(s, a, grid, smem, st));
-        else if (s->dq % 8 == 0 && !(getenv("BSR_LDG_U") && atoi(getenv("BSR_LDG_U")) == 4))
+        else if (s->dq % 8 == 0 && s->kn.ldg_u != 4)
             TRY(launch_scan<8>(s, a, grid, smem, st));
         else if (s->dq % 4 == 0) TRY(launch_scan<4>(s, a, grid, smem, st));
         else if (s->dq % 2 == 0) TRY(launch_scan<2>(s, a, grid, smem, st));
@@ -903,7 +983,7 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
     CU(cudaEventRecord(s->ev_scan1, st));
     s->scan_timed = true;
     if (fuse) return BSR_OK;
-    TRY(merge_tree(s, (const u64*)s->cta_keys.p, grid, nq, K, K, (size_t)grid * K, d_cand, st));
+    TRY(merge_tree(s, (const u64*)s->cta_keys.p, grid, nq, K, k, K, (size_t)grid * K, d_cand, st));
     if (d_idx) {
         unpack_kernel<<<nq, 128, 0, st>>>(d_cand, K, k, d_idx, d_dist, d_count);
         s->launches++;
@@ -927,7 +1007,9 @@ extern "C" int bsr_search_device(bsr_store* s, const float* d_queries, uint32_t 
     CHECK(d_candidates, BSR_ERR_INVALID, "bsr_search_device: null output");
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
-    return search_device_impl(s, d_queries, nq, k, (u64*)d_candidates, nullptr, nullptr, nullptr, st);
+    TRY(order_after_previous(s, st));
+    TRY(search_device_impl(s, d_queries, nq, k, (u64*)d_candidates, nullptr, nullptr, nullptr, st));
+    return mark_busy(s, st);
 }
 
 extern "C" int bsr_merge_device(bsr_store* s, const uint64_t* d_lists, uint32_t n_lists,
@@ -938,19 +1020,21 @@ extern "C" int bsr_merge_device(bsr_store* s, const uint64_t* d_lists, uint32_t 
     CHECK(d_out, BSR_ERR_INVALID, "bsr_merge_device: null output");
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
+    TRY(order_after_previous(s, st));
     const u32 K = bsr_candidate_slots(k);
     if (K == 32 && n_lists <= 4096) {  // one warp per query folds the lists in registers
         merge32_kernel<<<nq, 32, 0, st>>>((const u64*)d_lists, n_lists, (size_t)nq * K, K, k, (u64*)d_out, nullptr,
                                           nullptr, nullptr);
         s->launches++;
         CU(cudaGetLastError());
-        return BSR_OK;
+        return mark_busy(s, st);
     }
     const u32 max_per_cta = std::max<u32>(2, kMergeMaxKeys / K);
     const size_t inter = (size_t)nq * ((n_lists + max_per_cta - 1) / max_per_cta) * K * sizeof(u64);
     TRY(ensure(s->merge_a, inter));
     TRY(ensure(s->merge_b, inter));
-    return merge_tree(s, (const u64*)d_lists, n_lists, nq, K, (size_t)nq * K, K, (u64*)d_out, st);
+    TRY(merge_tree(s, (const u64*)d_lists, n_lists, nq, K, k, (size_t)nq * K, K, (u64*)d_out, st));
+    return mark_busy(s, st);
 }
 
 extern "C" int bsr_unpack_device(bsr_store* s, const uint64_t* d_cand, uint32_t nq, uint32_t k,
@@ -960,11 +1044,12 @@ extern "C" int bsr_unpack_device(bsr_store* s, const uint64_t* d_cand, uint32_t 
     CHECK(d_idx && d_dist && d_count, BSR_ERR_INVALID, "bsr_unpack_device: null output");
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
+    TRY(order_after_previous(s, st));
     unpack_kernel<<<nq, 128, 0, st>>>((const u64*)d_cand, bsr_candidate_slots(k), k, (u64*)d_idx,
                                       d_dist, d_count);
     s->launches++;
     CU(cudaGetLastError());
-    return BSR_OK;
+    return mark_busy(s, st);
 }
 
 extern "C" int bsr_search(bsr_store* s, const float* queries, uint32_t nq, uint32_t k,
@@ -992,6 +1077,7 @@ extern "C" int bsr_search(bsr_store* s, const float* queries, uint32_t nq, uint3
         memset(out_count, 0, cbytes);
         return BSR_OK;
     }
+    TRY(order_after_previous(s, s->stream));
     CU(cudaMemcpyAsync(s->d_queries.p, h, qbytes, cudaMemcpyHostToDevice, s->stream));
     // Small results (a few queries): the kernel that unpacks writes them straight into the pinned
     // host block (mapped into the device's address space under UVA) -- the D2H transfer still
@@ -1002,6 +1088,7 @@ extern "C" int bsr_search(bsr_store* s, const float* queries, uint32_t nq, uint3
                            (float*)(r + ibytes), (u32*)(r + ibytes + dbytes), s->stream));
     if (!direct) CU(cudaMemcpyAsync(h + off_r, r, rbytes, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
+    mark_idle(s);
     memcpy(out_idx, h + off_r, ibytes);
     memcpy(out_dist, h + off_r + ibytes, dbytes);
     memcpy(out_count, h + off_r + ibytes + dbytes, cbytes);
@@ -1022,6 +1109,42 @@ extern "C" int bsr_merge_host(bsr_store* s, const uint64_t* idx, const float* di
     for (u64 i = 0; i < n; i++)
         CHECK(idx[i] < 0xFFFFFFFFull, BSR_ERR_RANGE, "bsr_merge_host: index %llu does not fit 32 bits",
               (unsigned long long)idx[i]);
+    // HashSet de-dup of metrics.rs:156-168: after the stable sort the first occurrence of an index
+    // wins, i.e. its entry with the smallest (distance, position).  Shards own disjoint row blocks, so
+    // in the engine's own use there are no duplicates and this pass only looks; when there are, the
+    // losing entries are dropped before the pairs go to the device.
+    std::vector<uint64_t> dd_idx;
+    std::vector<float> dd_dist;
+    {
+        std::vector<u64> order(n);
+        for (u64 i = 0; i < n; i++) order[i] = i;
+        // partial_cmp order of the reference's sort_by (metrics.rs:153); NaN distances compare "equal" there,
+        // here they are ordered last so the choice is deterministic
+        auto less_dist = [&](u64 a, u64 b) {
+            const float x = dist[a], y = dist[b];
+            if (x != x || y != y) return (y != y) && !(x != x);
+            return x < y;
+        };
+        std::stable_sort(order.begin(), order.end(), [&](u64 a, u64 b) {
+            if (idx[a] != idx[b]) return idx[a] < idx[b];
+            return less_dist(a, b);
+        });
+        bool dup = false;
+        for (u64 i = 1; i < n && !dup; i++) dup = idx[order[i]] == idx[order[i - 1]];
+        if (dup) {
+            std::vector<char> keep(n, 0);
+            for (u64 i = 0; i < n; i++)
+                if (i == 0 || idx[order[i]] != idx[order[i - 1]]) keep[order[i]] = 1;
+            for (u64 i = 0; i < n; i++)
+                if (keep[i]) {
+                    dd_idx.push_back(idx[i]);
+                    dd_dist.push_back(dist[i]);
+                }
+            idx = dd_idx.data();
+            dist = dd_dist.data();
+            n = dd_idx.size();
+        }
+    }
     DeviceGuard g(s->device);
     const u32 K = bsr_candidate_slots(k);
     const u32 n_lists = (u32)((n + K - 1) / K);
@@ -1040,6 +1163,7 @@ extern "C" int bsr_merge_host(bsr_store* s, const uint64_t* idx, const float* di
     char* h = (char*)s->h_pinned;
     memcpy(h, idx, (size_t)n * sizeof(u64));
     memcpy(h + (size_t)n * sizeof(u64), dist, (size_t)n * sizeof(float));
+    TRY(order_after_previous(s, s->stream));
     CU(cudaMemcpyAsync(s->staging.p, h, in_bytes, cudaMemcpyHostToDevice, s->stream));
     const u64* d_i = (const u64*)s->staging.p;
     const float* d_d = (const float*)((char*)s->staging.p + (size_t)n * sizeof(u64));
@@ -1047,7 +1171,7 @@ extern "C" int bsr_merge_host(bsr_store* s, const uint64_t* idx, const float* di
                                                                                  (u64*)s->cta_keys.p);
     s->launches++;
     CU(cudaGetLastError());
-    TRY(merge_tree(s, (const u64*)s->cta_keys.p, n_lists, 1, K, K, (size_t)n_lists * K,
+    TRY(merge_tree(s, (const u64*)s->cta_keys.p, n_lists, 1, K, k, K, (size_t)n_lists * K,
                    (u64*)s->d_cand.p, s->stream));
     char* r = (char*)s->d_result.p;
     unpack_kernel<<<1, 128, 0, s->stream>>>((const u64*)s->d_cand.p, K, k, (u64*)r, (float*)(r + ibytes),
@@ -1056,6 +1180,7 @@ extern "C" int bsr_merge_host(bsr_store* s, const uint64_t* idx, const float* di
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h, r, rbytes, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
+    mark_idle(s);
     u32 cnt;
     memcpy(&cnt, h + ibytes + dbytes, sizeof(u32));
     memcpy(out_idx, h, (size_t)cnt * sizeof(u64));
@@ -1157,6 +1282,11 @@ extern "C" int bsr_comm_destroy(bsr_comm* c) {
 
 extern "C" int bsr_search_parallel(bsr_store* s, bsr_comm* c, const float* queries, uint32_t nq, uint32_t k,
                                    uint64_t* out_idx, float* out_dist, uint32_t* out_count) {
+    // Arguments every rank passes identically (or that are local programming errors) are rejected
+    // before any collective work.  Past that point a rank ALWAYS joins the exchange: a local failure
+    // (allocation, scan) turns its contribution into an empty list -- what the reference does with a
+    // failed local scan (metrics.rs:185-191) -- and the error is returned after the collective, so the
+    // other ranks are never left waiting.
     TRY(check_search_args(s, queries, nq, k, "bsr_search_parallel"));
     CHECK(c && c->comm, BSR_ERR_INVALID, "bsr_search_parallel: null communicator");
     CHECK(c->device == s->device, BSR_ERR_INVALID, "bsr_search_parallel: shard and communicator are on different devices");
@@ -1170,24 +1300,37 @@ extern "C" int bsr_search_parallel(bsr_store* s, bsr_comm* c, const float* queri
                  cbytes = (size_t)nq * sizeof(u32);
     const size_t rbytes = ibytes + dbytes + cbytes, off_r = (qbytes + 15) & ~(size_t)15;
     const size_t cand_bytes = (size_t)nq * K * sizeof(u64);
-    TRY(ensure_pinned(s, off_r + rbytes));
-    TRY(ensure(s->d_queries, qbytes));
+    // the two buffers the exchange itself needs; without them this rank cannot take part at all
     TRY(ensure(s->d_cand, cand_bytes));
     TRY(ensure(s->d_gather, cand_bytes * c->n_ranks + cand_bytes));
-    TRY(ensure(s->d_result, rbytes));
-    char* h = (char*)s->h_pinned;
-    memcpy(h, queries, qbytes);
-    CU(cudaMemcpyAsync(s->d_queries.p, h, qbytes, cudaMemcpyHostToDevice, s->stream));
-    if (s->n_rows == 0) {
-        // an empty shard contributes an empty list (metrics.rs:185-191): all slots UINT64_MAX
-        CU(cudaMemsetAsync(s->d_cand.p, 0xFF, cand_bytes, s->stream));
-    } else {
-        TRY(search_device_impl(s, (const float*)s->d_queries.p, nq, k, (u64*)s->d_cand.p, nullptr, nullptr,
-                               nullptr, s->stream));
+    TRY(order_after_previous(s, s->stream));
+
+    char* h = nullptr;
+    auto local_scan = [&]() -> int {
+        TRY(ensure_pinned(s, off_r + rbytes));
+        TRY(ensure(s->d_queries, qbytes));
+        TRY(ensure(s->d_result, rbytes));
+        h = (char*)s->h_pinned;
+        memcpy(h, queries, qbytes);
+        CU(cudaMemcpyAsync(s->d_queries.p, h, qbytes, cudaMemcpyHostToDevice, s->stream));
+        if (s->n_rows == 0) {
+            // an empty shard contributes an empty list (metrics.rs:36-52): all slots UINT64_MAX
+            CU(cudaMemsetAsync(s->d_cand.p, 0xFF, cand_bytes, s->stream));
+            return BSR_OK;
+        }
+        return search_device_impl(s, (const float*)s->d_queries.p, nq, k, (u64*)s->d_cand.p, nullptr, nullptr,
+                                  nullptr, s->stream);
+    };
+    int local_rc = local_scan();
+    char local_err[sizeof g_err];
+    if (local_rc != BSR_OK) {
+        memcpy(local_err, g_err, sizeof g_err);
+        // whatever the failed scan left behind must not reach the other ranks
+        if (cudaMemsetAsync(s->d_cand.p, 0xFF, cand_bytes, s->stream) != cudaSuccess) cudaGetLastError();
     }
     // rank-ordered concatenation of every rank's [nq][K] slots (displacements, metrics.rs:86-89)
     NCCL(nccl().AllGather(s->d_cand.p, s->d_gather.p, (size_t)nq * K, kNcclUint64, c->comm, s->stream));
-    if (root) {
+    auto root_merge = [&]() -> int {
         u64* merged = (u64*)((char*)s->d_gather.p + cand_bytes * c->n_ranks);
         const u32 max_per_cta = std::max<u32>(2, kMergeMaxKeys / K);
         const size_t inter = (size_t)nq * ((c->n_ranks + max_per_cta - 1) / max_per_cta) * K * sizeof(u64);
@@ -1200,7 +1343,7 @@ extern "C" int bsr_search_parallel(bsr_store* s, bsr_comm* c, const float* queri
                                                      nullptr, (u64*)r, (float*)(r + ibytes),
                                                      (u32*)(r + ibytes + dbytes));
         } else {
-            TRY(merge_tree(s, (const u64*)s->d_gather.p, (u32)c->n_ranks, nq, K, (size_t)nq * K, K, merged,
+            TRY(merge_tree(s, (const u64*)s->d_gather.p, (u32)c->n_ranks, nq, K, k, (size_t)nq * K, K, merged,
                            s->stream));
             unpack_kernel<<<nq, 128, 0, s->stream>>>(merged, K, k, (u64*)r, (float*)(r + ibytes),
                                                      (u32*)(r + ibytes + dbytes));
@@ -1209,8 +1352,17 @@ extern "C" int bsr_search_parallel(bsr_store* s, bsr_comm* c, const float* queri
         s->launches++;
         CU(cudaGetLastError());
         if (!direct) CU(cudaMemcpyAsync(h + off_r, r, rbytes, cudaMemcpyDeviceToHost, s->stream));
-    }
+        return BSR_OK;
+    };
+    int merge_rc = BSR_OK;
+    if (root && local_rc == BSR_OK) merge_rc = root_merge();
     CU(cudaStreamSynchronize(s->stream));
+    mark_idle(s);
+    if (local_rc != BSR_OK) {
+        memcpy(g_err, local_err, sizeof g_err);
+        return local_rc;
+    }
+    TRY(merge_rc);
     if (root) {
         memcpy(out_idx, h + off_r, ibytes);
         memcpy(out_dist, h + off_r + ibytes, dbytes);
@@ -1254,6 +1406,40 @@ extern "C" int bsr_store_scan_profile(bsr_store* s, double* total_ms, uint64_t* 
     *total_ms = s->prof_ms;
     *n_scans = s->prof_scans;
     return BSR_OK;
+}
+
+extern "C" int bsr_store_set_metric(bsr_store* s, bsr_metric metric) {
+    CHECK(s, BSR_ERR_INVALID, "bsr_store_set_metric: null store");
+    CHECK(metric == BSR_COSINE || metric == BSR_DOT, BSR_ERR_INVALID, "bsr_store_set_metric: bad metric %d", (int)metric);
+    s->metric = metric;
+    return BSR_OK;
+}
+
+extern "C" int bsr_store_metric(const bsr_store* s, bsr_metric* metric) {
+    CHECK(s && metric, BSR_ERR_INVALID, "bsr_store_metric: null argument");
+    *metric = s->metric;
+    return BSR_OK;
+}
+
+extern "C" int bsr_store_set_option(bsr_store* s, const char* name, int64_t value) {
+    CHECK(s && name, BSR_ERR_INVALID, "bsr_store_set_option: null argument");
+    const int v = (int)value;
+    struct { const char* name; int* field; } table[] = {
+        {"scan_ldg", &s->kn.scan_ldg},         {"ldg_u", &s->kn.ldg_u},
+        {"bulk_stages", &s->kn.bulk_stages},   {"max_qb", &s->kn.max_qb},
+        {"no_wide", &s->kn.no_wide},           {"no_fuse_wide", &s->kn.no_fuse_wide},
+        {"max_grid", &s->kn.max_grid},         {"tensor_mode", &s->kn.tensor_mode},
+        {"tensor_stages", &s->kn.tensor_stages}, {"tensor_stage_kb", &s->kn.tensor_stage_kb},
+        {"tc_stats", &s->kn.tc_stats},         {"no_pdl", &s->kn.no_pdl},
+        {"no_mailbox", &s->kn.no_mailbox},
+    };
+    for (auto& t : table)
+        if (strcmp(t.name, name) == 0) {
+            *t.field = v;
+            if (t.field == &s->kn.max_qb) s->kn.max_qb = std::max(1, v);
+            return BSR_OK;
+        }
+    return fail(BSR_ERR_INVALID, "bsr_store_set_option: unknown option '%s'", name);
 }
 
 extern "C" int bsr_store_set_tensor_min_batch(bsr_store* s, uint32_t min_batch) {

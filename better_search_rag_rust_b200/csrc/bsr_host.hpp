@@ -66,6 +66,14 @@ class GpuVectorstore {
     GpuVectorstore(const GpuVectorstore&) = delete;
     GpuVectorstore& operator=(const GpuVectorstore&) = delete;
 
+    // BSR_COSINE: the reference's cosine_distance (default); BSR_DOT: 1 - dot product
+    void set_metric(bsr_metric m) { check(bsr_store_set_metric(h_, m)); }
+    bsr_metric metric() const {
+        bsr_metric m;
+        check(bsr_store_metric(h_, &m));
+        return m;
+    }
+    void set_option(const char* name, int64_t value) { check(bsr_store_set_option(h_, name, value)); }
     void reset() { check(bsr_store_reset(h_)); }                                  // :93-95
     void append(const std::vector<float>& v) { append_many({v}); }                // :97-99
     void append_many(const std::vector<std::vector<float>>& vectors) {            // :101-119

@@ -45,6 +45,9 @@ __device__ __forceinline__ u64 make_key(float dist, u32 gidx) {
     // partial_cmp treats -0.0 and +0.0 as equal: canonicalise to +0.0 (cosine distances are
     // never -0.0 anyway).
     u32 b = __float_as_uint(__fadd_rn(dist, 0.0f));
+    // a NaN distance (BSR_DOT on NaN / inf*0 inputs; cosine distances are never NaN) sorts after
+    // every number whatever its sign bit: one canonical quiet NaN
+    if (dist != dist) b = 0x7FC00000u;
     return ((u64)ordered_from_bits(b) << 32) | (u64)gidx;
 }
 
@@ -133,8 +136,10 @@ __device__ __forceinline__ float sq4_seq(float acc, const float4& q) {
 }
 
 // src/metrics.rs:157-164 given dot, |a|, |b| and the identity flag (:148-151).
+// metric != 0 (BSR_DOT, include/bsr.h): 1 - dot, nothing else.
 __device__ __forceinline__ float finish_distance(float dot, float mag_a, float mag_b,
-                                                 bool identical) {
+                                                 bool identical, u32 metric = 0) {
+    if (metric) return __fsub_rn(1.0f, dot);
     if (identical) return 0.0f;
     if (mag_a == 0.0f || mag_b == 0.0f) return 1.0f;
     float sim = __fdiv_rn(dot, __fmul_rn(mag_a, mag_b));
@@ -519,7 +524,7 @@ __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta
             u32 valid = 0;
             for (u32 j = tid; j < K; j += W * 32) {
                 const u64 v = ql[j];
-                fo.keys[(size_t)q * K + j] = v;
+                fo.keys[(size_t)q * K + j] = j < k ? v : kKeyMax;  // slots past top_k are published empty
                 if (fo.idx && j < k) {
                     const bool ok = v != kKeyMax;
                     fo.idx[(size_t)q * k + j] = ok ? (v & 0xFFFFFFFFull) : 0ull;
@@ -568,7 +573,7 @@ __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta
         u64 v = lists[((size_t)q * W) * 32 + lane];
 #pragma unroll
         for (int w = 1; w < W; w++) v = warp_merge32(v, lists[((size_t)q * W + w) * 32 + lane], lane);
-        fo.keys[(size_t)q * 32 + lane] = v;
+        fo.keys[(size_t)q * 32 + lane] = (u32)lane < k ? v : kKeyMax;  // slots past top_k are published empty
         if (fo.idx) {
             const bool ok = (u32)lane < k && v != kKeyMax;
             if ((u32)lane < k) {
@@ -596,6 +601,7 @@ struct ScanArgs {
     u32 n_rows, n_panels, dq, dim, k, k_pad;
     u32 row_base;          // global index of local row 0
     u32 fuse_final;        // 1: the last CTA also merges all CTA lists and unpacks (requires k_pad <= 128)
+    u32 metric;            // bsr_metric: 0 cosine distance, 1 dot product (1 - dot)
     FinalOut fin;
     unsigned long long* dbg;  // debug builds (-DBSR_TC_TIMELINE): globaltimer stamps, else unused
 };
@@ -680,7 +686,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_f32_kernel(const Sc
                     dq, lane);
                 u64 key = kKeyMax;
                 if (row < a.n_rows)
-                    key = make_key(finish_distance(acc, mag_a, mag_b, identical), a.row_base + row);
+                    key = make_key(finish_distance(acc, mag_a, mag_b, identical, a.metric), a.row_base + row);
                 top.offer(key, lane);
             }
             if (!has_next) break;
@@ -995,7 +1001,7 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
                 const bool identical = valid && ((maybe_mask >> b) & 1u);
                 u64 key = kKeyMax;
                 if (valid)
-                    key = make_key(finish_distance(acc[b], mag_a, mag_b[b], identical), a.row_base + row);
+                    key = make_key(finish_distance(acc[b], mag_a, mag_b[b], identical, a.metric), a.row_base + row);
                 top[b].offer(key, lane);
             }
             ci = 0;
@@ -1023,7 +1029,7 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kMergeThreads) merge_lists_kernel(
     const u64* __restrict__ in, u32 n_lists, u32 K, u32 lists_per_cta, size_t list_stride,
-    size_t query_stride, u64* __restrict__ out) {
+    size_t query_stride, u64* __restrict__ out, u32 k_keep) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u64* buf = reinterpret_cast<u64*>(smem_raw);
     const u32 g = blockIdx.x, q = blockIdx.y;
@@ -1037,7 +1043,8 @@ __global__ void __launch_bounds__(kMergeThreads) merge_lists_kernel(
     __syncthreads();
     cta_merge_lists(buf, lists_per_cta, K);
     u64* o = out + ((size_t)q * gridDim.x + g) * K;
-    for (u32 j = threadIdx.x; j < K; j += blockDim.x) o[j] = buf[j];
+    // k_keep < K on the last level of a tree: slots past top_k are published empty (include/bsr.h)
+    for (u32 j = threadIdx.x; j < K; j += blockDim.x) o[j] = j < k_keep ? buf[j] : kKeyMax;
 }
 
 // (idx, dist) pairs -> candidate keys, cut into lists of K slots; a list must be ascending for the
@@ -1091,7 +1098,7 @@ __global__ void __launch_bounds__(32) merge32_kernel(const u64* __restrict__ in,
             if (their_best < my_worst) v = warp_merge32(v, t[i], lane);
         }
     }
-    if (out_keys) out_keys[(size_t)q * 32 + lane] = v;
+    if (out_keys) out_keys[(size_t)q * 32 + lane] = (u32)lane < k ? v : kKeyMax;
     if (idx) {
         const bool ok = (u32)lane < k && v != kKeyMax;
         if ((u32)lane < k) {

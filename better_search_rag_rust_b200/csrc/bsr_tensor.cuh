@@ -83,6 +83,8 @@ struct TensorScanArgs {
     u32 nq_valid;                // <= 128 * cluster size
     u32 n_rows, n_tiles, KB, dim, k, k_pad, row_base, stages;
     u32 stage_kb;                // 64-column blocks per ring stage (<= kTcStageKB)
+    u32 metric;                  // bsr_metric: 0 cosine (scores scaled by 1/|a|), 1 dot (inv_norms -> 64 ones, stride 0)
+    u32 norm_stride;             // rows between consecutive tiles' entries of norms / inv_norms (64, or 0 for BSR_DOT)
     long long* timeline;         // debug builds (-DBSR_TC_TIMELINE): [2 CTAs][kTlTiles][8] clock64 stamps
     u32 tl_start;                // first tile (position in the CTA's sequence) the timeline records
 };
@@ -280,6 +282,7 @@ __device__ __forceinline__ u64 pack_survivor(u32 row, float score) {
 __device__ __forceinline__ u64 survivor_key(const TensorScanArgs& a, u64 raw, float na, const float* qp, float mag_b) {
     const u32 row = (u32)(raw >> 32);
     const float score = __uint_as_float((u32)raw);
+    if (a.metric) return make_key(__fsub_rn(1.0f, score), a.row_base + row);  // BSR_DOT
     float dist = 1.0f;  // zero magnitude (src/metrics.rs:157-159)
     // identity (src/metrics.rs:148-151) precedes every other rule; within 1e-10 per element implies
     // sim ~ 1 unless the query is tiny (|b| < 1e-6), in which case every survivor is checked
@@ -400,9 +403,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
                     mbar_wait(smem_u32(nempty_bar + ns), ((sq / kTcNormSlots) & 1) ^ 1);
                     mbar_expect_tx(smem_u32(nfull_bar + ns), 2 * kTcN * sizeof(float));
                     float* dst = s_norm + (size_t)ns * 2 * kTcN;
-                    bulk_g2s(smem_u32(dst), a.norms + tile * kTcN, kTcN * sizeof(float),
+                    bulk_g2s(smem_u32(dst), a.norms + tile * a.norm_stride, kTcN * sizeof(float),
                              smem_u32(nfull_bar + ns), policy);
-                    bulk_g2s(smem_u32(dst + kTcN), a.inv_norms + tile * kTcN, kTcN * sizeof(float),
+                    bulk_g2s(smem_u32(dst + kTcN), a.inv_norms + tile * a.norm_stride, kTcN * sizeof(float),
                              smem_u32(nfull_bar + ns), policy);
                 }
                 for (u32 kb0 = 0; kb0 < KB; kb0 += SKB) {  // one copy per stage (several column blocks)
@@ -577,7 +580,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
         // The identity shortcut (src/metrics.rs:148-151) precedes every other rule.  Two vectors
         // within 1e-10 per element have sim ~ 1 unless the query itself is tiny (|b| < 1e-6): such
         // a query is never pruned and checks every row exactly.
-        const bool tiny_q = !(mag_b >= 1e-6f);
+        const bool tiny_q = !a.metric && !(mag_b >= 1e-6f);
 
         // classes: (row position in its tile) x (CTA group); this CTA owns 64 of the kc classes
         const u32 T = (a.k + kTcN - 1) / kTcN, kc = T * kTcN;
@@ -716,7 +719,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
                         }
                     }
                     // kc >= k distinct rows reach `bound`; keep a 1e-6 (in similarity) safety margin
-                    thr = (bound == -INFINITY) ? -INFINITY : bound - 1e-6f * mag_b - 1e-6f * fabsf(bound);
+                    // (BSR_DOT ranks by the raw score itself: t == S, so the margin only has to be >= 0)
+                    thr = (bound == -INFINITY) ? -INFINITY
+                                               : bound - (a.metric ? 0.0f : 1e-6f * mag_b) - 1e-6f * fabsf(bound);
                 }
             }
             if (tid == 0) BSR_TL(sq, 7);

@@ -239,6 +239,20 @@ class GpuVectorstore:
         """BF16 stores: smallest query batch that uses the tcgen05 path (0 = always exact scan)."""
         _lib.check(_lib.lib().bsr_store_set_tensor_min_batch(self.handle, int(min_batch)))
 
+    def set_metric(self, metric: str) -> None:
+        """"cosine" (the reference's cosine_distance, default) or "dot" (1 - dot product)."""
+        m = {"cosine": _lib.BSR_COSINE, "dot": _lib.BSR_DOT}[metric]
+        _lib.check(_lib.lib().bsr_store_set_metric(self.handle, m))
+
+    def metric(self) -> str:
+        m = C.c_int()
+        _lib.check(_lib.lib().bsr_store_metric(self.handle, C.byref(m)))
+        return {_lib.BSR_COSINE: "cosine", _lib.BSR_DOT: "dot"}[m.value]
+
+    def set_option(self, name: str, value: int) -> None:
+        """Ablation switch / test hook of this handle (bsr_store_set_option, include/bsr.h)."""
+        _lib.check(_lib.lib().bsr_store_set_option(self.handle, name.encode(), int(value)))
+
     def set_profiling(self, enabled: bool) -> None:
         _lib.check(_lib.lib().bsr_store_set_profiling(self.handle, 1 if enabled else 0))
 

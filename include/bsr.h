@@ -39,7 +39,7 @@ extern "C" {
 #define BSR_API
 #endif
 
-#define BSR_VERSION 100 /* 0.1.0 */
+#define BSR_VERSION 200 /* 0.2.0 */
 
 typedef enum bsr_status {
     BSR_OK = 0,
@@ -55,6 +55,16 @@ typedef enum bsr_dtype {
     BSR_BF16 = 1 /* rows rounded (RNE) to bfloat16 at load: half the HBM traffic; results equal
                     the reference arithmetic applied to the rounded rows */
 } bsr_dtype;
+
+/* Score a search ranks by.  The reference has cosine distance only (src/metrics.rs:143-165);
+ * BASELINE.json's north_star adds the dot product for stores that are normalised at ingest. */
+typedef enum bsr_metric {
+    BSR_COSINE = 0, /* cosine_distance, src/metrics.rs:143-165 (identity shortcut, zero-norm rule, clamp) */
+    BSR_DOT = 1     /* distance = 1 - dot(a, b): the reference's sequential binary32 fold of src/metrics.rs:153
+                       alone -- no norms, no clamp, no identity shortcut.  Equals the cosine distance on
+                       unit-norm rows and queries up to the rounding of the norms.  A NaN distance (NaN or
+                       inf*0 in the inputs) sorts after every number. */
+} bsr_metric;
 
 /* Largest top_k a search accepts (per-warp candidate lists live in shared memory). */
 #define BSR_MAX_TOP_K 1024u
@@ -94,6 +104,11 @@ BSR_API int bsr_store_append_device(bsr_store *store, const float *d_rows, uint6
 BSR_API int bsr_store_append_synthetic(bsr_store *store, uint64_t seed, uint64_t first_row,
                                uint64_t n_rows);
 
+/* Metric used by every search on this handle (default BSR_COSINE).  Takes effect from the next
+ * search; no data is touched (row norms are kept either way). */
+BSR_API int bsr_store_set_metric(bsr_store *store, bsr_metric metric);
+BSR_API int bsr_store_metric(const bsr_store *store, bsr_metric *metric);
+
 /* PolarsVectorstore::get_count (polars.rs:243-246). */
 BSR_API int bsr_store_count(const bsr_store *store, uint64_t *n_rows);
 BSR_API int bsr_store_dim(const bsr_store *store, uint32_t *dim);
@@ -128,7 +143,8 @@ BSR_API int bsr_search(bsr_store *store, const float *queries, uint32_t n_querie
 
 /* A candidate is one uint64: (order-preserving bits of the f32 distance) << 32 | global row
  * index.  Unsigned ascending order of candidates == the reference's (distance, index) order.
- * Each query owns bsr_candidate_slots(top_k) slots (a power of two >= 32); unused slots hold
+ * Each query owns bsr_candidate_slots(top_k) slots (a power of two >= 32); the first
+ * min(top_k, rows) slots hold the shard's top-k in ascending order, every other slot holds
  * UINT64_MAX. */
 BSR_API uint32_t bsr_candidate_slots(uint32_t top_k);
 
@@ -154,8 +170,10 @@ BSR_API int bsr_unpack_device(bsr_store *store, const uint64_t *d_candidates, ui
 
 /* compute_global_top_k (metrics.rs:141-171) with host buffers: the n gathered (index, distance)
  * pairs -- the rank-ordered concatenation gather_top_k_results builds at root -- are sorted on the
- * device by (distance, index) and the first min(top_k, n) written to out_idx/out_dist; *out_count
- * receives how many.  Indices must be < 2^32 - 1. */
+ * device by (distance, index) and the first min(top_k, distinct indices) written to
+ * out_idx/out_dist; *out_count receives how many.  An index that occurs more than once keeps its
+ * first occurrence in sorted order, as the reference's HashSet pass does (metrics.rs:156-168).
+ * Indices must be < 2^32 - 1. */
 BSR_API int bsr_merge_host(bsr_store *store, const uint64_t *idx, const float *dist, uint64_t n,
                            uint32_t top_k, uint64_t *out_idx, float *out_dist, uint32_t *out_count);
 
@@ -189,6 +207,15 @@ BSR_API int bsr_search_parallel(bsr_store *shard, bsr_comm *comm, const float *q
  * with the exact path to 2e-6 (4e-6 for rows nearly parallel to the query).  0 disables it: every search then uses the exact scan.  Needs dim <= 768 and
  * top_k <= 128; other shapes always use the exact scan. */
 BSR_API int bsr_store_set_tensor_min_batch(bsr_store *store, uint32_t min_batch);
+
+/* Ablation switches and test hooks, per handle (DESIGN.md lists them).  Defaults are the measured
+ * optimum; the same names upper-cased with a BSR_ prefix are read from the environment ONCE, when
+ * the library is first used, and seed every new handle.  Unknown name: BSR_ERR_INVALID.
+ *   "max_grid" n      cap the scan grid at n CTAs (test hook: long per-warp row streams on small stores)
+ *   "bulk_stages" n   ring depth of the bulk-async scan        "max_qb" n     widest exact query group
+ *   "scan_ldg" 0/1    register-staged scan kernel              "no_wide" 0/1  no 16-warp CTAs
+ *   "no_fuse_wide", "tensor_mode", "tensor_stages", "tensor_stage_kb", "tc_stats", "no_pdl", "no_mailbox" */
+BSR_API int bsr_store_set_option(bsr_store *store, const char *name, int64_t value);
 
 /* ---- introspection for the benchmark harness ---------------------------------------------- */
 

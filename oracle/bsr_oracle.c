@@ -7,13 +7,18 @@
  * baseline.  The product path (better_search_rag_rust_b200 + libbsr_b200.so)
  * never links, imports or calls it.
  *
- * PARITY UNPINNED: the reference (nichmorgan/better-search-rag-rust) holds no
- * golden vector, known-answer test or fixture for this path (no test calls
- * cosine_distance or any mpi_helpers::metrics function) and cannot be built here
- * (no cargo/rustc, no MPI).  This file is therefore a line-by-line restatement
- * of the reference source, checked against (i) hand-derived known answers,
- * (ii) the run-time self-query invariant of src/main.rs:111,120,148-154 and
- * (iii) an independent numpy restatement (oracle/numpy_oracle.py).
+ * PARITY UNPINNED for the search path proper: the reference
+ * (nichmorgan/better-search-rag-rust) holds no golden vector, known-answer test
+ * or fixture for it (no test calls cosine_distance or any mpi_helpers::metrics
+ * function) and cannot be built here (no cargo/rustc, no MPI).  This file is
+ * therefore a line-by-line restatement of the reference source, checked against
+ * (i) hand-derived known answers, (ii) the run-time self-query invariant of
+ * src/main.rs:111,120,148-154 and (iii) an independent numpy restatement
+ * (oracle/numpy_oracle.py).
+ * PINNED by the reference's own tests: vectors_are_identical and the three IR
+ * metrics built on it (mean_reciprocal_rank, recall_at_k, top_k_overlap) -- the
+ * known answers of src/metrics.rs:172-317 (1.0; ~0.611; 0.25/0.5/0.75/1.0; 0.8)
+ * are reproduced by tests/test_ir_metrics.py on inputs of the same construction.
  *
  * All arithmetic lives in the reference tree itself plus Rust core
  * (Iterator::sum::<f32>, f32::sqrt/max/min, slice::sort_by -- stable); the
@@ -92,6 +97,34 @@ BSR_EXPORT float bsr_oracle_cosine_distance(const float *a, uint64_t na,
 }
 
 /* ------------------------------------------------------------------------- */
+/* BSR_DOT (include/bsr.h; an extension, the reference has cosine only):      */
+/* distance = 1 - dot, dot being the fold of src/metrics.rs:153 alone.        */
+/* Length mismatch / empty input follow cosine_distance's first rule (:144).  */
+/* ------------------------------------------------------------------------- */
+BSR_EXPORT float bsr_oracle_dot_distance(const float *a, uint64_t na, const float *b,
+                                         uint64_t nb)
+{
+    if (na != nb || na == 0)
+        return 1.0f;
+    float dot = 0.0f;
+    for (uint64_t i = 0; i < na; i++)
+        dot = dot + a[i] * b[i];
+    return 1.0f - dot;
+}
+
+/* total order used for BSR_DOT distances: numbers ascending (-0 == +0), every
+ * NaN after every number (the order include/bsr.h documents) */
+static uint32_t ordered_bits(float d)
+{
+    uint32_t b;
+    d = d + 0.0f;
+    memcpy(&b, &d, 4);
+    if (d != d)
+        b = 0x7FC00000u;
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+/* ------------------------------------------------------------------------- */
 /* src/mpi_helpers/load_balance.rs:8-42  RankInterval / interval_by_rank      */
 /* ------------------------------------------------------------------------- */
 BSR_EXPORT void bsr_oracle_interval_by_rank(int32_t rank, int32_t size, uint64_t count,
@@ -143,7 +176,14 @@ typedef struct {
     float dist;
 } pair_t;
 
-static void stable_sort_pairs(pair_t *v, uint64_t n)
+static inline int pair_less(const pair_t *x, const pair_t *y, int total_order)
+{
+    if (total_order)
+        return ordered_bits(x->dist) < ordered_bits(y->dist);
+    return x->dist < y->dist; /* partial_cmp: the reference's comparator */
+}
+
+static void stable_sort_pairs_ord(pair_t *v, uint64_t n, int total_order)
 {
     if (n < 2)
         return;
@@ -156,7 +196,7 @@ static void stable_sort_pairs(pair_t *v, uint64_t n)
             uint64_t i = lo, j = mid, o = lo;
             while (i < mid && j < hi) {
                 /* take the right element only when strictly smaller: stability */
-                if (src[j].dist < src[i].dist)
+                if (pair_less(&src[j], &src[i], total_order))
                     dst[o++] = src[j++];
                 else
                     dst[o++] = src[i++];
@@ -180,11 +220,28 @@ static void stable_sort_pairs(pair_t *v, uint64_t n)
 /*   rows: the WHOLE global store, row-major [count][dim] (every rank opens    */
 /*   global.parquet, :23).  Returns the number of pairs written (<= top_k).    */
 /* ------------------------------------------------------------------------- */
+BSR_EXPORT uint64_t bsr_oracle_compute_local_top_k_metric(const float *rows, uint64_t count,
+                                                          uint32_t dim, int32_t rank, int32_t size,
+                                                          uint64_t top_k, const float *target,
+                                                          uint32_t target_len, int metric,
+                                                          uint64_t *out_idx, float *out_dist);
+
 BSR_EXPORT uint64_t bsr_oracle_compute_local_top_k(const float *rows, uint64_t count,
                                                    uint32_t dim, int32_t rank, int32_t size,
                                                    uint64_t top_k, const float *target,
                                                    uint32_t target_len, uint64_t *out_idx,
                                                    float *out_dist)
+{
+    return bsr_oracle_compute_local_top_k_metric(rows, count, dim, rank, size, top_k, target,
+                                                 target_len, 0, out_idx, out_dist);
+}
+
+/* metric: 0 = cosine_distance (the reference), 1 = BSR_DOT */
+BSR_EXPORT uint64_t bsr_oracle_compute_local_top_k_metric(const float *rows, uint64_t count,
+                                                          uint32_t dim, int32_t rank, int32_t size,
+                                                          uint64_t top_k, const float *target,
+                                                          uint32_t target_len, int metric,
+                                                          uint64_t *out_idx, float *out_dist)
 {
     uint64_t start, end, first, n;
     bsr_oracle_interval_by_rank(rank, size, count, &start, &end); /* :27 */
@@ -194,10 +251,11 @@ BSR_EXPORT uint64_t bsr_oracle_compute_local_top_k(const float *rows, uint64_t c
     pair_t *d = (pair_t *)malloc(n * sizeof(pair_t));
     for (uint64_t i = 0; i < n; i++) { /* :36-44 */
         d[i].idx = start + i;          /* :41 global index */
-        d[i].dist = bsr_oracle_cosine_distance(rows + (first + i) * (uint64_t)dim, dim, target,
-                                               target_len);
+        const float *row = rows + (first + i) * (uint64_t)dim;
+        d[i].dist = metric ? bsr_oracle_dot_distance(row, dim, target, target_len)
+                           : bsr_oracle_cosine_distance(row, dim, target, target_len);
     }
-    stable_sort_pairs(d, n); /* :47 */
+    stable_sort_pairs_ord(d, n, metric != 0); /* :47 */
     uint64_t keep = n > top_k ? top_k : n; /* :48-50 */
     for (uint64_t i = 0; i < keep; i++) {
         out_idx[i] = d[i].idx;
@@ -212,10 +270,24 @@ BSR_EXPORT uint64_t bsr_oracle_compute_local_top_k(const float *rows, uint64_t c
 /*   input: the rank-ordered concatenation gather_top_k_results builds at     */
 /*   root (:86-126).                                                          */
 /* ------------------------------------------------------------------------- */
+BSR_EXPORT uint64_t bsr_oracle_compute_global_top_k_metric(const uint64_t *global_idx,
+                                                           const float *global_dist, uint64_t n,
+                                                           uint64_t top_k, int metric,
+                                                           uint64_t *out_idx, float *out_dist);
+
 BSR_EXPORT uint64_t bsr_oracle_compute_global_top_k(const uint64_t *global_idx,
                                                     const float *global_dist, uint64_t n,
                                                     uint64_t top_k, uint64_t *out_idx,
                                                     float *out_dist)
+{
+    return bsr_oracle_compute_global_top_k_metric(global_idx, global_dist, n, top_k, 0, out_idx,
+                                                  out_dist);
+}
+
+BSR_EXPORT uint64_t bsr_oracle_compute_global_top_k_metric(const uint64_t *global_idx,
+                                                           const float *global_dist, uint64_t n,
+                                                           uint64_t top_k, int metric,
+                                                           uint64_t *out_idx, float *out_dist)
 {
     if (n == 0 || top_k == 0)
         return 0;
@@ -224,7 +296,7 @@ BSR_EXPORT uint64_t bsr_oracle_compute_global_top_k(const uint64_t *global_idx,
         g[i].idx = global_idx[i];
         g[i].dist = global_dist[i];
     }
-    stable_sort_pairs(g, n); /* :153 */
+    stable_sort_pairs_ord(g, n, metric != 0); /* :153 */
 
     /* :156-168 HashSet de-dup on the index, first top_k survivors. */
     uint64_t cap = 16;
@@ -337,6 +409,97 @@ BSR_EXPORT uint64_t bsr_oracle_parallel_top_k_similarity_search(
 }
 
 /* ------------------------------------------------------------------------- */
+/* src/metrics.rs:21-141  mean_reciprocal_rank / recall_at_k / top_k_overlap   */
+/*   A Vec<Vec<Vec<f32>>> arrives flattened: results[q] is n_results[q]        */
+/*   vectors of `dim` floats, queries back to back.  (The reference's ids_map   */
+/*   argument only feeds an unused binding, :38-41,79-82, so it has no effect   */
+/*   and no counterpart here.)                                                 */
+/* ------------------------------------------------------------------------- */
+BSR_EXPORT float bsr_oracle_mean_reciprocal_rank(const float *queries, uint64_t n_queries,
+                                                 const float *results,
+                                                 const uint64_t *n_results,
+                                                 uint64_t n_result_lists, uint32_t dim)
+{
+    if (n_queries == 0 || n_result_lists == 0 || n_queries != n_result_lists) /* :26-28 */
+        return 0.0f;
+    float sum = 0.0f;
+    float total = (float)n_queries;
+    const float *r = results;
+    for (uint64_t q = 0; q < n_queries; q++) { /* :33-55 */
+        uint64_t rank = 0;
+        for (uint64_t i = 0; i < n_results[q]; i++) {
+            if (bsr_oracle_vectors_are_identical(queries + q * (uint64_t)dim, dim,
+                                                 r + i * (uint64_t)dim, dim)) {
+                rank = i + 1;
+                break;
+            }
+        }
+        if (rank == 0)
+            rank = n_results[q] + 1; /* :50-52 */
+        sum += 1.0f / (float)rank;
+        r += n_results[q] * (uint64_t)dim;
+    }
+    return sum / total;
+}
+
+BSR_EXPORT float bsr_oracle_recall_at_k(const float *queries, uint64_t n_queries,
+                                        const float *results, const uint64_t *n_results,
+                                        uint64_t n_result_lists, uint32_t dim, uint64_t k)
+{
+    if (n_queries == 0 || n_result_lists == 0 || n_queries != n_result_lists) /* :66-68 */
+        return 0.0f;
+    float sum = 0.0f;
+    float total = (float)n_queries;
+    const float *r = results;
+    for (uint64_t q = 0; q < n_queries; q++) { /* :73-93 */
+        uint64_t actual_k = k < n_results[q] ? k : n_results[q];
+        int found = 0;
+        for (uint64_t i = 0; i < actual_k; i++) {
+            if (bsr_oracle_vectors_are_identical(queries + q * (uint64_t)dim, dim,
+                                                 r + i * (uint64_t)dim, dim)) {
+                found = 1;
+                break;
+            }
+        }
+        sum += found ? 1.0f : 0.0f;
+        r += n_results[q] * (uint64_t)dim;
+    }
+    return sum / total;
+}
+
+BSR_EXPORT float bsr_oracle_top_k_overlap(const float *seq, const uint64_t *n_seq,
+                                          uint64_t n_seq_lists, const float *par,
+                                          const uint64_t *n_par, uint64_t n_par_lists,
+                                          uint32_t dim, uint64_t k)
+{
+    if (n_seq_lists == 0 || n_par_lists == 0 || n_seq_lists != n_par_lists) /* :103-108 */
+        return 0.0f;
+    float sum = 0.0f;
+    float total = (float)n_seq_lists;
+    const float *s = seq, *p = par;
+    for (uint64_t q = 0; q < n_seq_lists; q++) { /* :113-138 */
+        uint64_t m = n_seq[q] < n_par[q] ? n_seq[q] : n_par[q];
+        uint64_t actual_k = k < m ? k : m;
+        if (actual_k != 0) {
+            uint64_t overlap = 0;
+            for (uint64_t i = 0; i < actual_k; i++) {
+                for (uint64_t j = 0; j < actual_k; j++) {
+                    if (bsr_oracle_vectors_are_identical(s + i * (uint64_t)dim, dim,
+                                                         p + j * (uint64_t)dim, dim)) {
+                        overlap++;
+                        break;
+                    }
+                }
+            }
+            sum += (float)overlap / (float)actual_k;
+        }
+        s += n_seq[q] * (uint64_t)dim;
+        p += n_par[q] * (uint64_t)dim;
+    }
+    return sum / total;
+}
+
+/* ------------------------------------------------------------------------- */
 /* src/mpi_helpers/metrics.rs:217-249  calculate_accuracy_metrics             */
 /* ------------------------------------------------------------------------- */
 BSR_EXPORT void bsr_oracle_calculate_accuracy_metrics(const uint64_t *idx, uint64_t n,
@@ -384,6 +547,47 @@ BSR_EXPORT void bsr_oracle_generate_rows(uint64_t seed, uint64_t first_row, uint
     }
 }
 
+/* compute_local_top_k (src/mpi_helpers/metrics.rs:36-50) over generator rows
+ * [first_row, first_row + n_rows) WITHOUT materialising them: rows are produced
+ * 2048 at a time, every row's distance is kept, then the same stable sort and
+ * truncate.  Indices are first_row + i, i.e. global generator rows.  This is what
+ * lets bench.py check a 12.5 M-row shard in full with a few MB of host memory.
+ * bf16 != 0: rows are rounded to bfloat16 first (the BSR_BF16 store's content). */
+BSR_EXPORT void bsr_oracle_round_bf16(const float *in, uint64_t n, float *out);
+
+BSR_EXPORT uint64_t bsr_oracle_scan_generated(uint64_t seed, uint64_t first_row, uint64_t n_rows,
+                                              uint32_t dim, int bf16, int metric, uint64_t top_k,
+                                              const float *target, uint32_t target_len,
+                                              uint64_t *out_idx, float *out_dist)
+{
+    if (n_rows == 0)
+        return 0;
+    const uint64_t chunk = 2048;
+    float *buf = (float *)malloc(chunk * (uint64_t)dim * sizeof(float));
+    pair_t *d = (pair_t *)malloc(n_rows * sizeof(pair_t));
+    for (uint64_t lo = 0; lo < n_rows; lo += chunk) {
+        uint64_t n = n_rows - lo < chunk ? n_rows - lo : chunk;
+        bsr_oracle_generate_rows(seed, first_row + lo, n, dim, buf);
+        if (bf16)
+            bsr_oracle_round_bf16(buf, n * (uint64_t)dim, buf);
+        for (uint64_t i = 0; i < n; i++) {
+            const float *row = buf + i * (uint64_t)dim;
+            d[lo + i].idx = first_row + lo + i;
+            d[lo + i].dist = metric ? bsr_oracle_dot_distance(row, dim, target, target_len)
+                                    : bsr_oracle_cosine_distance(row, dim, target, target_len);
+        }
+    }
+    stable_sort_pairs_ord(d, n_rows, metric != 0);
+    uint64_t keep = n_rows > top_k ? top_k : n_rows;
+    for (uint64_t i = 0; i < keep; i++) {
+        out_idx[i] = d[i].idx;
+        out_dist[i] = d[i].dist;
+    }
+    free(d);
+    free(buf);
+    return keep;
+}
+
 /* round-to-nearest-even f32 -> bf16 -> f32, the quantisation the bf16 store applies */
 BSR_EXPORT void bsr_oracle_round_bf16(const float *in, uint64_t n, float *out)
 {
@@ -401,4 +605,4 @@ BSR_EXPORT void bsr_oracle_round_bf16(const float *in, uint64_t n, float *out)
     }
 }
 
-BSR_EXPORT int bsr_oracle_version(void) { return 1; }
+BSR_EXPORT int bsr_oracle_version(void) { return 2; }

@@ -119,15 +119,94 @@ def _distances(rows: np.ndarray, target: np.ndarray) -> np.ndarray:
     return dist
 
 
-def compute_local_top_k(rows, rank: int, size: int, top_k: int, target):
-    """src/mpi_helpers/metrics.rs:16-53"""
+def dot_distance(a, b) -> np.float32:
+    """BSR_DOT (include/bsr.h): 1 - the fold of src/metrics.rs:153 alone."""
+    a = np.asarray(a, dtype=F32).ravel()
+    b = np.asarray(b, dtype=F32).ravel()
+    if a.size != b.size or a.size == 0:
+        return F32(1.0)
+    with np.errstate(all="ignore"):
+        return F32(F32(1.0) - _seq_sum_f32(a * b))
+
+
+def _dot_distances(rows: np.ndarray, target: np.ndarray) -> np.ndarray:
+    rows = np.asarray(rows, dtype=F32)
+    target = np.asarray(target, dtype=F32).ravel()
+    n, d = rows.shape
+    if d != target.size or d == 0:
+        return np.full(n, 1.0, dtype=F32)
+    with np.errstate(all="ignore"):
+        dot = np.add.accumulate(rows * target[None, :], axis=1, dtype=F32)[:, -1]
+        return (F32(1.0) - dot).astype(F32)
+
+
+def _ordered_bits(d: np.ndarray) -> np.ndarray:
+    """total order of BSR_DOT distances: numbers ascending, -0 == +0, every NaN last"""
+    d = (np.asarray(d, dtype=F32) + F32(0.0)).astype(F32)
+    b = d.view(np.uint32).copy()
+    b[np.isnan(d)] = np.uint32(0x7FC00000)
+    return np.where(b & np.uint32(0x80000000), ~b, b | np.uint32(0x80000000)).astype(np.uint32)
+
+
+def compute_local_top_k(rows, rank: int, size: int, top_k: int, target, metric: int = 0):
+    """src/mpi_helpers/metrics.rs:16-53 (metric 1: BSR_DOT distances in their total order)"""
     rows = np.asarray(rows, dtype=F32)
     first, n = effective_block(rank, size, rows.shape[0])
     if n == 0:
         return np.zeros(0, np.uint64), np.zeros(0, F32)
-    dist = _distances(rows[first:first + n], target)
-    order = np.argsort(dist, kind="stable")[:top_k]  # stable sort + truncate (:47-50)
+    if metric:
+        dist = _dot_distances(rows[first:first + n], target)
+        order = np.argsort(_ordered_bits(dist), kind="stable")[:top_k]
+    else:
+        dist = _distances(rows[first:first + n], target)
+        order = np.argsort(dist, kind="stable")[:top_k]  # stable sort + truncate (:47-50)
     return (order + first).astype(np.uint64), dist[order]
+
+
+def mean_reciprocal_rank(queries, results) -> np.float32:
+    """src/metrics.rs:21-58 (ids_map only feeds an unused binding there)."""
+    if len(queries) == 0 or len(results) == 0 or len(queries) != len(results):
+        return F32(0.0)
+    total = F32(0.0)
+    for q, res in zip(queries, results):
+        rank = 0
+        for i, r in enumerate(res):
+            if vectors_are_identical(q, r):
+                rank = i + 1
+                break
+        if rank == 0:
+            rank = len(res) + 1
+        total = F32(total + F32(F32(1.0) / F32(rank)))
+    return F32(total / F32(len(queries)))
+
+
+def recall_at_k(queries, results, k: int) -> np.float32:
+    """src/metrics.rs:60-96"""
+    if len(queries) == 0 or len(results) == 0 or len(queries) != len(results):
+        return F32(0.0)
+    total = F32(0.0)
+    for q, res in zip(queries, results):
+        found = any(vectors_are_identical(q, res[i]) for i in range(min(k, len(res))))
+        total = F32(total + F32(1.0 if found else 0.0))
+    return F32(total / F32(len(queries)))
+
+
+def top_k_overlap(sequential_results, parallel_results, k: int) -> np.float32:
+    """src/metrics.rs:98-141"""
+    if (len(sequential_results) == 0 or len(parallel_results) == 0
+            or len(sequential_results) != len(parallel_results)):
+        return F32(0.0)
+    total = F32(0.0)
+    for seq, par in zip(sequential_results, parallel_results):
+        actual_k = min(k, len(seq), len(par))
+        if actual_k == 0:
+            continue
+        overlap = 0
+        for i in range(actual_k):
+            if any(vectors_are_identical(seq[i], par[j]) for j in range(actual_k)):
+                overlap += 1
+        total = F32(total + F32(F32(overlap) / F32(actual_k)))
+    return F32(total / F32(len(sequential_results)))
 
 
 def compute_global_top_k(global_idx, global_dist, top_k: int):

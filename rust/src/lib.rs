@@ -24,6 +24,8 @@ pub mod ffi {
     pub const BSR_OK: c_int = 0;
     pub const BSR_F32: c_int = 0;
     pub const BSR_BF16: c_int = 1;
+    pub const BSR_COSINE: c_int = 0;
+    pub const BSR_DOT: c_int = 1;
     pub const BSR_MAX_TOP_K: u32 = 1024;
 
     extern "C" {
@@ -39,6 +41,8 @@ pub mod ffi {
         pub fn bsr_store_append_device(store: *mut bsr_store, d_rows: *const f32, n_rows: u64) -> c_int;
         pub fn bsr_store_append_synthetic(store: *mut bsr_store, seed: u64, first_row: u64,
                                           n_rows: u64) -> c_int;
+        pub fn bsr_store_set_metric(store: *mut bsr_store, metric: c_int) -> c_int;
+        pub fn bsr_store_metric(store: *const bsr_store, metric: *mut c_int) -> c_int;
         pub fn bsr_store_count(store: *const bsr_store, n_rows: *mut u64) -> c_int;
         pub fn bsr_store_dim(store: *const bsr_store, dim: *mut u32) -> c_int;
         pub fn bsr_store_row_base(store: *const bsr_store, row_base: *mut u64) -> c_int;
@@ -70,6 +74,7 @@ pub mod ffi {
                                    n_queries: u32, top_k: u32, out_idx: *mut u64, out_dist: *mut f32,
                                    out_count: *mut u32) -> c_int;
         pub fn bsr_store_set_tensor_min_batch(store: *mut bsr_store, min_batch: u32) -> c_int;
+        pub fn bsr_store_set_option(store: *mut bsr_store, name: *const c_char, value: i64) -> c_int;
         pub fn bsr_store_launch_count(store: *const bsr_store, n_launches: *mut u64) -> c_int;
         pub fn bsr_store_last_scan_ms(store: *mut bsr_store, ms: *mut f32) -> c_int;
         pub fn bsr_store_set_profiling(store: *mut bsr_store, enabled: c_int) -> c_int;
@@ -132,6 +137,12 @@ impl GpuVectorstore {
     }
 
     /// polars.rs:93-95
+    /// `dot = false`: the reference's cosine_distance (default); `dot = true`: 1 - dot product
+    /// (BSR_DOT, for stores normalised at ingest).
+    pub fn set_dot_metric(&mut self, dot: bool) -> Result<(), BsrError> {
+        check(unsafe { ffi::bsr_store_set_metric(self.handle, if dot { ffi::BSR_DOT } else { ffi::BSR_COSINE }) })
+    }
+
     pub fn reset(&mut self) -> Result<(), BsrError> {
         check(unsafe { ffi::bsr_store_reset(self.handle) })
     }

@@ -60,7 +60,7 @@ def test_header_compiles_as_c_and_cxx(tmp_path):
 
 def test_constants_and_slots():
     L = _lib.lib()
-    assert L.bsr_version() == 100
+    assert L.bsr_version() == 200
     assert [L.bsr_candidate_slots(k) for k in (1, 10, 32, 33, 50, 100, 1000, 1024)] == \
         [32, 32, 32, 64, 64, 128, 1024, 1024]
     assert L.bsr_candidate_slots(0) == 0 and L.bsr_candidate_slots(1025) == 0

@@ -222,34 +222,29 @@ def test_query_batch_through_the_abi():
     store.close()
 
 
-# ---- full size (BASELINE.json configs[1]): size-independent properties -----------------------------
-def test_one_million_rows_properties():
-    n, k = 1_000_000, 10
-    store = bsr.GpuVectorstore(None, True, dim=768, capacity_rows=n)
+# ---- full size (BASELINE.json configs[1]): the complete list against the oracle ----------------------
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_one_million_rows_full_compare(dtype):
+    """1 M x 768, the whole top-k against the oracle run over the regenerated rows (block-wise on the
+    host threads, oracle/c_oracle.py::scan_generated_parallel -- about a second of CPU time)."""
+    n = 1_000_000
+    store = bsr.GpuVectorstore(None, True, dim=768, capacity_rows=n, dtype=dtype)
     store.append_synthetic(SEED, 0, n)
+    store.set_tensor_min_batch(0)
     eng = bsr.CudaShardEngine(store)
+    threads = max(1, len(os.sched_getaffinity(0)))
     q = co.generate_rows(SEED + 0x1000, 0, 1, 768)[0]
     for query, self_query in ((store.get(0), True), (q, False)):
-        top = bsr.compute_local_top_k(None, 0, 1, k, query, engine=eng)
-        idx = [p[0] for p in top]
-        dist = np.array([p[1] for p in top], F)
-        assert len(set(idx)) == k and all(0 <= i < n for i in idx)
-        keys = S.pack_candidates(idx, dist, k)
-        assert np.all(np.diff(keys.astype(object)) > 0)            # ascending (distance, index)
-        if self_query:
-            assert top[0] == (0, 0.0)
-        # every reported distance is the oracle's distance for that (regenerated) row
-        for i, d in top:
-            row = co.generate_rows(SEED, i, 1, 768)[0]
-            assert _bits(co.cosine_distance(row, query)) == _bits(d)
-        # nothing in a 60k-row sample beats the k-th result; sample rows that belong are reported
-        lo = 470_000
-        sample = co.generate_rows(SEED, lo, 60_000, 768)
-        si, sd = co.compute_local_top_k(sample, 0, 1, k, query)
-        s_keys = S.pack_candidates(si + np.uint64(lo), sd, k)
-        better = s_keys[s_keys < keys[-1]]
-        assert set(better.tolist()) <= set(keys.tolist())
-        # a block-sharded search over the same store gives the same list (merge is associative)
-        top4 = bsr.compute_local_top_k(None, 0, 1, 4 * k, query, engine=eng)
-        assert top4[:k] == top
+        for k in (10, 50):
+            top = bsr.compute_local_top_k(None, 0, 1, k, query, engine=eng)
+            wi, wd = co.scan_generated_parallel(SEED, 0, n, k, query, threads=threads, bf16=(dtype == "bf16"))
+            _assert_pairs(top, wi, _bits(wd))
+            if self_query:
+                assert top[0] == (0, 0.0)
+    # ... and as one batch of four through the shared pass
+    qs = np.stack([store.get(0), q, store.get(999_999), co.generate_rows(SEED + 0x1001, 0, 1, 768)[0]])
+    idx, dist, cnt = eng.local_top_k(qs, 10)
+    for i in range(4):
+        wi, wd = co.scan_generated_parallel(SEED, 0, n, 10, qs[i], threads=threads, bf16=(dtype == "bf16"))
+        assert idx[i].tolist() == wi.tolist() and _bits(dist[i]).tolist() == _bits(wd).tolist()
     store.close()

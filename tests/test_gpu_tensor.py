@@ -79,12 +79,11 @@ def test_tensor_path_other_dim_and_edge_rows():
 
 
 @pytest.mark.parametrize("nq,k,n", [(40, 10, 20000), (200, 10, 20000), (40, 100, 6000)])
-def test_tensor_path_adversarial_row_order_overflows_the_survivor_buffers(nq, k, n, monkeypatch):
+def test_tensor_path_adversarial_row_order_overflows_the_survivor_buffers(nq, k, n):
     """Rows sorted by *increasing* similarity to the queries: every new row beats the running bound,
-    so nothing is pruned and -- with the grid capped to one cluster (BSR_MAX_GRID, a test hook) --
+    so nothing is pruned and -- with the grid capped to one cluster (`max_grid`, a test hook) --
     each (cluster, query) survivor list overflows its 1 024 slots many times.  The overflow path
     (`compact_survivors`: keep exactly the best k of the buffer) must still give the oracle's list."""
-    monkeypatch.setenv("BSR_MAX_GRID", "2")
     dim = 768
     base = co.generate_rows(SEED + 11, 0, 1, dim)[0]
     noise = co.generate_rows(SEED + 12, 0, n, dim)
@@ -93,6 +92,7 @@ def test_tensor_path_adversarial_row_order_overflows_the_survivor_buffers(nq, k,
     st = bsr.GpuVectorstore(None, True, dtype="bf16")
     st.append_many(rows)
     st.set_tensor_min_batch(32)
+    st.set_option("max_grid", 2)
     eng = bsr.CudaShardEngine(st)
     rr = co.round_bf16(rows)
     qs = (base[None, :] + 0.02 * co.generate_rows(SEED + 13, 0, nq, dim)).astype(np.float32)
@@ -102,4 +102,38 @@ def test_tensor_path_adversarial_row_order_overflows_the_survivor_buffers(nq, k,
     # lose up to one ulp of the running sum -- the tensor core truncates -- i.e. up to 48 * 2^-24 =
     # 2.9e-6 in similarity, one-sided (measured here: 1.0e-6 .. 2.1e-6).  Stated bound for this case: 4e-6.
     _check(idx, dist, cnt, rr, co.round_bf16(qs), k, TOL=4e-6)
+    st.close()
+
+
+@pytest.mark.parametrize("nq", [512, 1024])
+def test_tensor_path_at_the_benchmark_shape(nq):
+    """BASELINE.json configs[2]'s own shape class: bf16 store, CTA pairs (MODE 2, cta_group::2),
+    top-100 (two class groups, kc = 128), several back-to-back 256-query launches sharing the
+    class-maxima and survivor scratch -- on 1 M rows, a sample of 20 queries spread over all launches
+    against the threaded oracle (regenerated rows, rounded to bf16 like the store)."""
+    import os
+    n, k = 1_000_000, 100
+    st = bsr.GpuVectorstore(None, True, dim=768, capacity_rows=n, dtype="bf16")
+    st.append_synthetic(SEED, 0, n)
+    st.set_tensor_min_batch(32)
+    eng = bsr.CudaShardEngine(st)
+    qs = co.generate_rows(SEED + 0x3000, 0, nq, 768)
+    qs[0] = st.get(0)                                # self-query, first launch
+    qs[nq - 1] = st.get(n - 1)                       # self-query, last launch, last row of the store
+    qr = co.round_bf16(qs)
+    idx, dist, cnt = eng.local_top_k(qs, k)
+    assert idx[0, 0] == 0 and dist[0, 0] == 0.0
+    assert idx[nq - 1, 0] == n - 1 and dist[nq - 1, 0] == 0.0
+    threads = max(1, len(os.sched_getaffinity(0)))
+    sample = sorted(set([0, 1, 127, 128, 255, 256, 257, nq // 2, nq - 2, nq - 1] +
+                        list(range(3, nq, max(1, nq // 10)))))
+    assert len(sample) >= 16
+    for i in sample:
+        wi, wd = co.scan_generated_parallel(SEED, 0, n, k, qr[i], threads=threads, bf16=True)
+        gi, gd = idx[i, :cnt[i]], dist[i, :cnt[i]]
+        assert cnt[i] == k and np.all(np.diff(gd) >= 0) and len(set(gi.tolist())) == k
+        assert np.max(np.abs(gd - wd)) <= TOL, (i, np.max(np.abs(gd - wd)))
+        for j in np.nonzero(gi != wi)[0]:
+            row = co.round_bf16(co.generate_rows(SEED, int(gi[j]), 1, 768))[0]
+            assert abs(float(co.cosine_distance(row, qr[i])) - float(wd[j])) <= TOL, (i, j, gi[j], wi[j])
     st.close()

@@ -2,8 +2,8 @@
 
 On stores small enough for the CPU oracle a full grid gives every warp at most a few panels, so
 its K-slot list never fills and the steady-state path (threshold test, K == 32: in-place insert,
-K > 32: batched block merge, `WarpTopK::flush`) would go untested.  BSR_MAX_GRID (a test hook read
-by the library on every search) caps the grid so that each warp scans thousands of rows."""
+K > 32: batched block merge, `WarpTopK::flush`) would go untested.  The `max_grid` option (a
+per-handle test hook, bsr_store_set_option) caps the grid so that each warp scans thousands of rows."""
 import os
 
 import numpy as np
@@ -21,8 +21,7 @@ def _bits(x):
 
 
 @pytest.fixture
-def small_grid(request, monkeypatch):
-    monkeypatch.setenv("BSR_MAX_GRID", str(request.param))
+def small_grid(request):
     yield request.param
 
 
@@ -38,6 +37,7 @@ def test_steady_state_topk_matches_oracle(small_grid, dtype):
     st = bsr.GpuVectorstore(None, True, dtype=dtype)
     st.append_many(rows)
     st.set_tensor_min_batch(0)
+    st.set_option("max_grid", small_grid)
     eng = bsr.CudaShardEngine(st)
     ref_rows = co.round_bf16(rows) if dtype == "bf16" else rows
     for k in (10, 33, 50, 100, 300, 1024):

@@ -191,3 +191,52 @@ def test_oracle_reproduces_edge_golden():
                 idx, dist = co.parallel_top_k_similarity_search(rows, int(size), int(k), q)
                 assert np.array_equal(idx, g[f"idx_q{qi}_k{k}_s{size}"])
                 assert np.array_equal(bits(dist), g[f"dist_bits_q{qi}_k{k}_s{size}"])
+
+
+# ---- BSR_DOT (an extension: the reference has cosine only) ---------------------------------------
+def test_dot_distance_known_answers_and_order():
+    assert co.dot_distance([1, 2, 3], [4, 5, 6]) == F(1.0) - F(32.0)
+    assert co.dot_distance([1, 0], [0, 1]) == 1.0
+    assert co.dot_distance([1, 2], [1, 2, 3]) == 1.0 and co.dot_distance([], []) == 1.0
+    # sequential fold, separately rounded products: same value as the numpy restatement, bit for bit
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        a, b = rng.uniform(-1, 1, 768).astype(F), rng.uniform(-1, 1, 768).astype(F)
+        assert bits(co.dot_distance(a, b)) == bits(no.dot_distance(a, b))
+    # on unit vectors it is the cosine distance up to the rounding of the norms
+    a /= np.linalg.norm(a); b /= np.linalg.norm(b)
+    assert abs(float(co.dot_distance(a, b)) - float(co.cosine_distance(a, b))) < 1e-6
+    # total order: numbers ascending, NaN after +inf, ties by index
+    rows = np.array([[1, 0], [np.nan, 0], [-3e38, -3e38], [3e38, 3e38], [1, 0], [0, 0]], F)
+    idx, dist = co.compute_local_top_k(rows, 0, 1, 6, np.array([3e38, 3e38], F), metric=1)
+    assert idx.tolist() == [3, 0, 4, 5, 2, 1]
+    assert dist[0] == -np.inf and dist[4] == np.inf and np.isnan(dist[5])
+
+
+def test_oracle_reproduces_dot_golden():
+    g = np.load(os.path.join(GOLDEN, "dot_metric.npz"))
+    rows, queries = g["rows"], g["queries"]
+    for qi, q in enumerate(queries):
+        assert np.array_equal(bits([no.dot_distance(r, q) for r in rows]), g[f"all_dist_bits_q{qi}"])
+        for k in g["ks"]:
+            for size in g["sizes"]:
+                parts = [no.compute_local_top_k(rows, r, int(size), int(k), q, metric=1) for r in range(int(size))]
+                gi, gd = co.compute_global_top_k(np.concatenate([p[0] for p in parts]),
+                                                 np.concatenate([p[1] for p in parts]), int(k), metric=1)
+                assert np.array_equal(gi, g[f"idx_q{qi}_k{k}_s{size}"])
+                assert np.array_equal(bits(gd), g[f"dist_bits_q{qi}_k{k}_s{size}"])
+
+
+def test_scan_generated_equals_materialised_scan():
+    """bench.py's full-size parity check walks generator rows block-wise; on a size the plain oracle
+    also handles, the block-wise list must be the plain one (every block size, threads, bf16)."""
+    n, k = 5000, 50
+    rows = co.generate_rows(0x5EED0001, 100, n, 768)
+    q = co.generate_rows(0x5EED0001 + 0x1000, 0, 1, 768)[0]
+    wi, wd = co.compute_local_top_k(rows, 0, 1, k, q)
+    for block, threads in ((n, 1), (777, 1), (1024, 4)):
+        gi, gd = co.scan_generated_parallel(0x5EED0001, 100, n, k, q, threads=threads, block_rows=block)
+        assert (gi - 100).tolist() == wi.tolist() and np.array_equal(bits(gd), bits(wd))
+    wi, wd = co.compute_local_top_k(co.round_bf16(rows), 0, 1, k, q, metric=1)
+    gi, gd = co.scan_generated_parallel(0x5EED0001, 100, n, k, q, threads=2, block_rows=999, bf16=True, metric=1)
+    assert (gi - 100).tolist() == wi.tolist() and np.array_equal(bits(gd), bits(wd))
