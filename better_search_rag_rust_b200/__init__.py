@@ -15,7 +15,7 @@ from .search import (ROOT, BsrComm, CudaShardEngine, candidate_slots, compute_gl
                      compute_local_top_k, gather_top_k_results, is_root, open_shard,
                      pack_candidates, parallel_top_k_similarity_search, release_shards,
                      unpack_candidates)
-from .vectorstore import (GpuVectorstore, NoDataError, SliceArgs, get_global_vstore,  # noqa: F401
-                          get_local_vstore)
+from .vectorstore import (GpuVectorstore, NoDataError, ParquetRowSource, SliceArgs,  # noqa: F401
+                          get_global_vstore, get_local_vstore, rank_file_paths)
 
 __version__ = "0.2.0"

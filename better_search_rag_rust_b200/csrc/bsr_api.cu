@@ -75,6 +75,8 @@ struct Knobs {
     int tensor_stages = 0;   // BSR_TENSOR_STAGES
     int tensor_stage_kb = 0; // BSR_TENSOR_STAGE_KB
     int tc_stats = 0;        // BSR_TC_STATS
+    int wide = -1;           // BSR_WIDE: 16-warp CTAs: -1 auto (small f32 stores, every bf16 store), 0 never, 1 always
+    int no_tickets = 0;      // BSR_NO_TICKETS: static panel deal on large stores too
     int no_pdl = 0;          // BSR_NO_PDL: plain stream-ordered launches for back-to-back scans
     int no_mailbox = 0;      // BSR_NO_MAILBOX: cross-rank exchange through ncclAllGather only
 };
@@ -97,6 +99,8 @@ static const Knobs& knobs() {
         v.tensor_stages = geti("BSR_TENSOR_STAGES", 0);
         v.tensor_stage_kb = geti("BSR_TENSOR_STAGE_KB", 0);
         v.tc_stats = getenv("BSR_TC_STATS") != nullptr;
+        v.wide = geti("BSR_WIDE", -1);
+        v.no_tickets = getenv("BSR_NO_TICKETS") != nullptr;
         v.no_pdl = getenv("BSR_NO_PDL") != nullptr;
         v.no_mailbox = getenv("BSR_NO_MAILBOX") != nullptr;
         return v;
@@ -134,6 +138,11 @@ struct bsr_store {
     u32 tensor_min_batch = 32;  // BF16 stores: batches at least this large use the tcgen05 path (0 = never)
     void* h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
+    // upload pipeline of bsr_store_append: two pinned host blocks + the two halves of `staging`, so the
+    // host-side copy of block i+1 overlaps the H2D transfer and the re-layout kernel of block i
+    void* h_stage[2] = {nullptr, nullptr};
+    size_t h_stage_bytes = 0;
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
 
     u64 launches = 0;
     // All calls on a handle share one scratch set (cta_keys, merge buffers, the last-CTA ticket).  The
@@ -332,6 +341,10 @@ extern "C" int bsr_store_destroy(bsr_store* s) {
     if (s->norms) cudaFree(s->norms);
     if (s->inv_norms) cudaFree(s->inv_norms);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    for (int i = 0; i < 2; i++) {
+        if (s->h_stage[i]) cudaFreeHost(s->h_stage[i]);
+        if (s->ev_stage[i]) cudaEventDestroy(s->ev_stage[i]);
+    }
     for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
     if (s->ev_busy) cudaEventDestroy(s->ev_busy);
     if (s->ev_scan0) cudaEventDestroy(s->ev_scan0);
@@ -411,24 +424,52 @@ extern "C" int bsr_store_append_device(bsr_store* s, const float* d_rows, uint64
     return finish_append(s, n_rows);
 }
 
+// Upload block: large enough to run PCIe at full rate, small enough to keep the pinned footprint modest.
+constexpr size_t kUploadBlockBytes = 32ull << 20;
+
+static int ensure_upload_pipeline(bsr_store* s, size_t block_bytes) {
+    if (s->h_stage_bytes >= block_bytes) return BSR_OK;
+    for (int i = 0; i < 2; i++) {
+        if (s->h_stage[i]) CU(cudaFreeHost(s->h_stage[i]));
+        s->h_stage[i] = nullptr;
+    }
+    s->h_stage_bytes = 0;
+    for (int i = 0; i < 2; i++) {
+        CU(cudaMallocHost(&s->h_stage[i], block_bytes));
+        if (!s->ev_stage[i]) CU(cudaEventCreateWithFlags(&s->ev_stage[i], cudaEventDisableTiming));
+    }
+    s->h_stage_bytes = block_bytes;
+    return BSR_OK;
+}
+
 extern "C" int bsr_store_append(bsr_store* s, const float* rows, uint64_t n_rows) {
     CHECK(s, BSR_ERR_INVALID, "bsr_store_append: null store");
     if (n_rows == 0) return BSR_OK;
     CHECK(rows, BSR_ERR_INVALID, "bsr_store_append: null rows");
     TRY(check_room(s, n_rows));
     DeviceGuard g(s->device);
+    TRY(order_after_previous(s, s->stream));
     TRY(reserve_rows(s, s->n_rows + n_rows));
+    // caller's (pageable) rows -> pinned block -> device staging -> re-layout kernel, two blocks in
+    // flight: while block i crosses PCIe and is interleaved into the panels, the host fills block i+1
     const size_t row_bytes = (size_t)s->dim * sizeof(float);
-    const u64 chunk_rows = std::max<u64>(1, std::min<u64>(n_rows, (256ull << 20) / row_bytes));
-    TRY(ensure(s->staging, (size_t)chunk_rows * row_bytes));
-    for (u64 done = 0; done < n_rows; done += chunk_rows) {
-        const u64 n = std::min(chunk_rows, n_rows - done);
-        CU(cudaMemcpyAsync(s->staging.p, rows + done * s->dim, (size_t)n * row_bytes,
-                           cudaMemcpyHostToDevice, s->stream));
-        TRY(interleave_from_device(s, (const float*)s->staging.p, s->n_rows + done, n));
-        CU(cudaStreamSynchronize(s->stream));
+    const u64 block_rows = std::max<u64>(1, std::min<u64>(n_rows, kUploadBlockBytes / row_bytes));
+    const size_t block_bytes = (size_t)block_rows * row_bytes;
+    TRY(ensure_upload_pipeline(s, block_bytes));
+    TRY(ensure(s->staging, 2 * block_bytes));
+    bool used[2] = {false, false};
+    int b = 0;
+    for (u64 done = 0; done < n_rows; done += block_rows, b ^= 1) {
+        const u64 n = std::min(block_rows, n_rows - done);
+        if (used[b]) CU(cudaEventSynchronize(s->ev_stage[b]));  // block b's previous contents are on the device
+        memcpy(s->h_stage[b], rows + done * s->dim, (size_t)n * row_bytes);
+        float* d_block = (float*)((char*)s->staging.p + (size_t)b * block_bytes);
+        CU(cudaMemcpyAsync(d_block, s->h_stage[b], (size_t)n * row_bytes, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaEventRecord(s->ev_stage[b], s->stream));  // the pinned block may be refilled from here on
+        TRY(interleave_from_device(s, d_block, s->n_rows + done, n));
+        used[b] = true;
     }
-    return finish_append(s, n_rows);
+    return finish_append(s, n_rows);  // norms of the new rows; synchronises the stream
 }
 
 extern "C" int bsr_store_append_synthetic(bsr_store* s, uint64_t seed, uint64_t first_row,
@@ -613,7 +654,7 @@ static u32 bulk_max_qb(const bsr_store* s, u32 K) {
 
 template <int QB, bool BF16, int W = kBulkWarps>
 static int launch_scan_bulk_t(bsr_store* s, const ScanArgs& a, unsigned grid, u32 stages, u32 active_warps,
-                              cudaStream_t st) {
+                              cudaStream_t st, u32* panel_ticket = nullptr) {
     static thread_local bool configured[64] = {false};
     if (!configured[s->device & 63]) {
         cudaFuncAttributes fa;
@@ -627,6 +668,7 @@ static int launch_scan_bulk_t(bsr_store* s, const ScanArgs& a, unsigned grid, u3
     ba.stages = stages;
     ba.active_warps = active_warps;
     ba.interleave = 1u;  // panels dealt over CTAs first: the ring is sized for active_warps on that assumption
+    ba.panel_ticket = panel_ticket;
     scan_topk_bulk_kernel<QB, BF16, W>
         <<<grid, W * 32, bulk_smem_bytes(s, a.k_pad, stages, QB, active_warps, W), st>>>(ba);
     s->launches++;
@@ -636,9 +678,9 @@ static int launch_scan_bulk_t(bsr_store* s, const ScanArgs& a, unsigned grid, u3
 
 template <int QB>
 static int launch_scan_bulk(bsr_store* s, const ScanArgs& a, unsigned grid, u32 stages, u32 active_warps,
-                            cudaStream_t st) {
-    return is_bf16(s) ? launch_scan_bulk_t<QB, true>(s, a, grid, stages, active_warps, st)
-                      : launch_scan_bulk_t<QB, false>(s, a, grid, stages, active_warps, st);
+                            cudaStream_t st, u32* panel_ticket) {
+    return is_bf16(s) ? launch_scan_bulk_t<QB, true>(s, a, grid, stages, active_warps, st, panel_ticket)
+                      : launch_scan_bulk_t<QB, false>(s, a, grid, stages, active_warps, st, panel_ticket);
 }
 
 // reduce n_lists lists per query to one; returns the buffer holding [nq][K] in *result
@@ -876,10 +918,16 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
     if (s->kn.max_grid) grid_cap = std::max(1u, std::min<unsigned>(grid_cap, (unsigned)s->kn.max_grid));
     const unsigned grid = bulk ? std::max(1u, std::min<unsigned>(grid_cap, n_panels))
                                : std::min<unsigned>(grid_cap, scan_grid(s, n_panels, kScanWarps));
-    // small stores (more than one, at most four rounds of panels at 8 warps per CTA): 16 warps per CTA
+    // 16 warps per CTA (single queries): small fp32 stores (more than one, at most four rounds of
+    // panels at 8 warps per CTA), where a second round on a few warps would double the latency-bound
+    // run time; and EVERY bf16 store -- a bf16 warp needs ~2.7x the instructions per byte (widening) and
+    // is bound by its dependent-issue latency at two warps per scheduler (ncu: 0.47 IPC per scheduler,
+    // 4.3 cycles between a warp's instructions, 5.0 of 7.2 TB/s): four warps per scheduler hide it.
     const u32 per_cta = (n_panels + grid - 1) / grid;
-    const bool wide = bulk && per_cta > (u32)kBulkWarps && per_cta <= 4u * kBulkWarps &&
-                      bulk_stages(s, K, 1, std::min<u32>(16, per_cta), true, 16) >= 2 && !s->kn.no_wide;
+    const bool wide_fits = bulk && per_cta > (u32)kBulkWarps &&
+                           bulk_stages(s, K, 1, std::min<u32>(16, per_cta), per_cta <= 32u, 16) >= 2;
+    const bool wide_auto = per_cta <= 4u * kBulkWarps || is_bf16(s);
+    const bool wide = wide_fits && !s->kn.no_wide && (s->kn.wide < 0 ? wide_auto : s->kn.wide != 0);
     const u32 active_warps = std::min<u32>(wide ? 16u : (u32)kBulkWarps, per_cta);
     const bool small_store = n_panels <= 2u * grid * (wide ? 16u : (u32)kBulkWarps);
     const size_t smem = (size_t)s->dq * sizeof(float4) + (size_t)kScanWarps * K * sizeof(u64);
@@ -894,6 +942,10 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
         TRY(ensure(s->d_counter, 256));
         CU(cudaMemsetAsync(s->d_counter.p, 0, 256, st));
     }
+    // large stores: panels after a warp's first are dealt by ticket (BulkScanArgs::panel_ticket); the
+    // kernel's single-panel lookahead needs a ring no deeper than a panel has chunks
+    const u32 cpp = is_bf16(s) ? s->kb : (s->dq + kChunkQuads - 1) / kChunkQuads;
+    u32* const ticket = (u32*)s->d_counter.p + 16;
     const u32 max_per_cta = std::max<u32>(2, kMergeMaxKeys / K);
     const size_t inter = (size_t)nq * ((grid + max_per_cta - 1) / max_per_cta) * K * sizeof(u64);
     TRY(ensure(s->merge_a, inter));
@@ -943,18 +995,21 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
         if (bulk) {
             if (qb == 1 && wide) {
                 const u32 stages = bulk_stages(s, K, 1, active_warps, small_store, 16);
-                if (is_bf16(s)) TRY((launch_scan_bulk_t<1, true, 16>(s, a, grid, stages, active_warps, st)));
-                else TRY((launch_scan_bulk_t<1, false, 16>(s, a, grid, stages, active_warps, st)));
+                u32* const tk = (!small_store && !s->kn.no_tickets && stages <= cpp) ? ticket : nullptr;
+                if (is_bf16(s)) TRY((launch_scan_bulk_t<1, true, 16>(s, a, grid, stages, active_warps, st, tk)));
+                else TRY((launch_scan_bulk_t<1, false, 16>(s, a, grid, stages, active_warps, st, tk)));
                 TRY(prof_end(s, st));
                 q += qb;
                 continue;
             }
             const u32 aw8 = std::min<u32>(kBulkWarps, active_warps);
-            const u32 stages = bulk_stages(s, K, qb, aw8, n_panels <= 2u * grid * kBulkWarps);
-            if (qb == 8) TRY(launch_scan_bulk<8>(s, a, grid, stages, aw8, st));
-            else if (qb == 4) TRY(launch_scan_bulk<4>(s, a, grid, stages, aw8, st));
-            else if (qb == 2) TRY(launch_scan_bulk<2>(s, a, grid, stages, aw8, st));
-            else TRY(launch_scan_bulk<1>(s, a, grid, stages, aw8, st));
+            const bool small8 = n_panels <= 2u * grid * kBulkWarps;
+            const u32 stages = bulk_stages(s, K, qb, aw8, small8);
+            u32* const tk = (!small8 && !s->kn.no_tickets && stages <= cpp) ? ticket : nullptr;
+            if (qb == 8) TRY(launch_scan_bulk<8>(s, a, grid, stages, aw8, st, tk));
+            else if (qb == 4) TRY(launch_scan_bulk<4>(s, a, grid, stages, aw8, st, tk));
+            else if (qb == 2) TRY(launch_scan_bulk<2>(s, a, grid, stages, aw8, st, tk));
+            else TRY(launch_scan_bulk<1>(s, a, grid, stages, aw8, st, tk));
         } else if (s->dq % 16 == 0 && s->kn.ldg_u == 16)
             TRY(launch_scan<16>(s, a, grid, smem, st));
         else if (s->dq % 8 == 0 && s->kn.ldg_u != 4)
@@ -972,6 +1027,8 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
                                           "last: lists folded", "last: done"};
             fprintf(stderr, "scan timeline (ns since cta0 start), grid %u:", grid);
             for (int i = 0; i < 11; i++) fprintf(stderr, " [%s %lld]", names[i], h_dbg[i] ? (long long)(h_dbg[i] - h_dbg[0]) : -1LL);
+            if (h_dbg[13] > h_dbg[12] && h_dbg[4] > h_dbg[0])
+                fprintf(stderr, " [SM clock %.0f MHz over the panel loop]", (double)(h_dbg[13] - h_dbg[12]) * 1e3 / (double)(h_dbg[4] - h_dbg[0]));
             fprintf(stderr, "\n  chunk wait->ready:");
             for (int i = 0; i < 24; i++)
                 fprintf(stderr, " %lld->%lld", (long long)(h_dbg[16 + 2 * i] - h_dbg[0]), (long long)(h_dbg[17 + 2 * i] - h_dbg[0]));
@@ -1431,6 +1488,7 @@ extern "C" int bsr_store_set_option(bsr_store* s, const char* name, int64_t valu
         {"max_grid", &s->kn.max_grid},         {"tensor_mode", &s->kn.tensor_mode},
         {"tensor_stages", &s->kn.tensor_stages}, {"tensor_stage_kb", &s->kn.tensor_stage_kb},
         {"tc_stats", &s->kn.tc_stats},         {"no_pdl", &s->kn.no_pdl},
+        {"wide", &s->kn.wide},                 {"no_tickets", &s->kn.no_tickets},
         {"no_mailbox", &s->kn.no_mailbox},
     };
     for (auto& t : table)

@@ -469,7 +469,7 @@ __device__ __forceinline__ void fold_cta_lists(const u64* src, u32 n_lists, u64 
 // merges every CTA's list and unpacks the result, so a whole search is one kernel.
 template <int W, int NQ>
 __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta_keys,
-                                              const FinalOut& fo, bool fuse_final) {
+                                              const FinalOut& fo, bool fuse_final, u32* panel_ticket = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ u32 s_is_last;
     const size_t q_stride = (size_t)gridDim.x * K;  // between queries in cta_keys
@@ -489,7 +489,7 @@ __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta
         }
     }
     BSR_STAMP(fo.dbg, blockIdx.x == 0 && tid == 0, 6);
-    if (!fuse_final) return;
+    if (!fuse_final && !panel_ticket) return;
 
     __threadfence();
     __syncthreads();
@@ -497,6 +497,11 @@ __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta
     __syncthreads();
     BSR_STAMP(fo.dbg, blockIdx.x == 0 && tid == 0, 7);
     if (!s_is_last) return;
+    if (panel_ticket && tid == 0) *panel_ticket = 0;  // every CTA has drawn its last ticket: ready for the next launch
+    if (!fuse_final) {
+        if (tid == 0) *fo.done_counter = 0;
+        return;
+    }
     BSR_STAMP(fo.dbg, tid == 0, 8);
     __threadfence();
     if (K != 32) {
@@ -518,6 +523,7 @@ __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta
             }
         }
         __syncthreads();
+        BSR_STAMP(fo.dbg, tid == 0, 9);
         for (int q = 0; q < NQ; q++) {
             u64* ql = lists + (size_t)q * W * K;
             cta_merge_lists(ql, W, K);  // ends with __syncthreads()
@@ -542,6 +548,7 @@ __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta
             }
         }
         if (tid == 0) *fo.done_counter = 0;
+        BSR_STAMP(fo.dbg, tid == 0, 10);
         return;
     }
     // K == 32: every warp folds a strided subset of the CTA lists in registers, per query
@@ -752,11 +759,28 @@ __device__ __forceinline__ void bulk_g2s(u32 dst, const void* src, u32 bytes, u3
         : "memory");
 }
 
+// Relaxed ticket draw whose result is first needed a whole panel later.  Around an atomic add on a
+// provably warp-uniform address ptxas builds its warp-aggregation pattern (vote, ATOMG by one lane,
+// SHFL of the result -- also for inline PTX, also for atom.inc), and that shuffle waits for the atomic's
+// L2 round trip on the spot.  Callers therefore pass `counter + z`, z being a zero the compiler cannot
+// prove uniform (read from shared memory at a per-lane address).
+__device__ __forceinline__ u32 draw_ticket(u32* counter) {
+    u32 r;
+    asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], 1;" : "=r"(r) : "l"(counter) : "memory");
+    return r;
+}
+
 struct BulkScanArgs {
     ScanArgs s;
     u32 stages;        // ring depth per warp (>= 2)
     u32 active_warps;  // warps per CTA that own at least one panel (the ring is sized for these)
     u32 interleave;    // 1: panels dealt round-robin over CTAs first (small stores); 0: over a CTA's warps first
+    // Dynamic panel dealing (large stores): every warp's first panel is static, every later one is
+    // the next ticket of this counter (ticket t = panel gridDim.x * W + t).  SMs do not all see the
+    // same HBM bandwidth; with a static deal the launch ends when the slowest SM does (a ~3 % spread
+    // of the scan time), with tickets it ends within one panel time (~16 us).  nullptr: static deal.
+    // Zero before the launch; the last CTA to finish resets it (needs ScanArgs::fin.done_counter).
+    u32* panel_ticket;
 };
 
 // QB queries share one pass over the store: the row chunk is read from shared memory once and
@@ -771,6 +795,9 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
     constexpr int CH = kChunkQuads;                    // fp32: column-quads per 4 KiB chunk
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BSR_STAMP(a.dbg, blockIdx.x == 0 && threadIdx.x == 0, 0);
+#ifdef BSR_TC_TIMELINE
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[12] = (unsigned long long)clock64();
+#endif
     const u32 dq = a.dq, S = ba.stages, K = a.k_pad;
     // [ring: active_warps*S*4KiB | queries: dq*QB*16, sq[j*QB + b] = column-quad j of query b (one
     //  address register per quad, the query index is an immediate offset) | lists: QB*W*K*8 |
@@ -793,39 +820,55 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
     const u32 panel0 = ba.interleave ? warp * gridDim.x + blockIdx.x : blockIdx.x * W + warp;
     const u32 KB = dq >> 4;                                      // bf16: 64-column blocks
     const u32 cpp = BF16 ? KB : (dq + CH - 1) / CH;              // chunks per 32-row panel
-    const u32 my_panels = panel0 < a.n_panels ? (a.n_panels - 1 - panel0) / total_warps + 1 : 0;
-    const u32 n_chunks = my_panels * cpp;
     const size_t panel_stride = (size_t)dq * 32;                 // fp32 layout, float4 units
     const u64 policy = make_evict_first_policy();
+    const bool dyn = ba.panel_ticket != nullptr;                 // host: only with S <= cpp (see below)
+    const u32 first_ticket_panel = gridDim.x * W;
 
-    // producer state (meaningful in lane 0): next chunk to request
-    u32 ic = 0, ipanel = panel0, ici = 0;
+    // Request cursor, warp-uniform (every lane keeps it; lane 0 alone talks to the copy engine): the
+    // panel being requested, the chunk inside it, the ring slot.  The cursor moves to the next panel
+    // lazily, on the first request that needs it, so after S <= cpp requests beyond the chunk being
+    // consumed it is at most ONE panel ahead of the consumer -- which is how the consumer learns its
+    // next panel in the dynamic deal.  Lane 0 draws the ticket for the panel after `ipanel` as soon as
+    // `ipanel` is known: the atomic's round trip is hidden behind a whole panel of requests.
+    __shared__ u32 s_zero[32];  // see draw_ticket
+    if (tid < 32) s_zero[tid] = 0;
+    u32 ipanel = panel0, ici = 0, islot = 0, inext = 0;
+    u32* my_ticket = ba.panel_ticket;  // + s_zero[lane] once shared memory is initialised (below)
     auto issue = [&]() {
-        const u32 st = ic % S;
-        const void* src;
-        u32 bytes;
-        if (BF16) {  // this warp's 32-row half of tile (ipanel/2), column block ici
-            src = store_b + ((size_t)(ipanel >> 1) * KB + ici) * kTileBytes + (ipanel & 1u) * 4096u;
-            bytes = 4096;
-        } else {
-            src = a.panels + (size_t)ipanel * panel_stride + (size_t)ici * CH * 32;
-            bytes = min((u32)CH, dq - ici * CH) * 512;
-        }
-        mbar_expect_tx(bar0 + st * 8, bytes);
-        bulk_g2s(ring + st * kChunkBytes, src, bytes, bar0 + st * 8, policy);
-        ic++;
-        if (++ici == cpp) {
+        if (ici == cpp) {
             ici = 0;
-            ipanel += total_warps;
+            if (dyn) {
+                ipanel = __shfl_sync(0xFFFFFFFFu, inext, 0);
+                if (lane == 0 && ipanel < a.n_panels) inext = first_ticket_panel + draw_ticket(my_ticket);
+            } else {
+                ipanel += total_warps;
+            }
         }
+        if (ipanel >= a.n_panels) return;  // nothing left to request
+        if (lane == 0) {
+            const void* src;
+            u32 bytes;
+            if (BF16) {  // this warp's 32-row half of tile (ipanel/2), column block ici
+                src = store_b + ((size_t)(ipanel >> 1) * KB + ici) * kTileBytes + (ipanel & 1u) * 4096u;
+                bytes = 4096;
+            } else {
+                src = a.panels + (size_t)ipanel * panel_stride + (size_t)ici * CH * 32;
+                bytes = min((u32)CH, dq - ici * CH) * 512;
+            }
+            mbar_expect_tx(bar0 + islot * 8, bytes);
+            bulk_g2s(ring + islot * kChunkBytes, src, bytes, bar0 + islot * 8, policy);
+        }
+        ici++;
+        if (++islot == S) islot = 0;
     };
     if (lane == 0) {
         for (u32 st = 0; st < S; st++) mbar_init(bar0 + st * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        const u32 pre = min(S, n_chunks);
-        for (u32 i = 0; i < pre; i++) issue();
     }
+    __syncwarp();
+    for (u32 i = 0; i < S; i++) issue();
 
     // stage the queries, zero-padded to the padded column count
     for (u32 t = tid; t < (u32)QB * dq; t += (W * 32)) {
@@ -844,6 +887,10 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
     BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 1);
     __syncthreads();
     BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 2);
+    if (dyn) {  // first draw: the ticket for this warp's second panel (the requests so far are all in the first)
+        my_ticket = ba.panel_ticket + s_zero[lane];
+        if (lane == 0 && panel0 < a.n_panels) inext = first_ticket_panel + draw_ticket(my_ticket);
+    }
 
     // |b| per query: accumulated by every thread during its first panel (src/metrics.rs:155)
     float mag_b[QB], qsq[QB], acc[QB];
@@ -856,7 +903,7 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
     // bit b: every column of my row seen so far is within 1e-10 of query b's.  Seeded from the first
     // columns of a panel, cleared chunk by chunk (only lanes with a live bit run the compare)
     unsigned maybe_mask = 0;
-    for (u32 c = 0; c < n_chunks; c++) {
+    for (u32 c = 0; panel < a.n_panels; c++) {
         if (ci == 0) {
             const u32 row = panel * kPanelRows + lane;
             mag_a = (row < a.n_rows) ? __ldg(a.norms + row) : 0.0f;
@@ -879,14 +926,28 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
                 for (int b = 0; b < QB; b++)
                     maybe_mask |= differs8_bf16(v0, sq[b], sq[(1) * QB + b]) ? 0u : (1u << b);
             }
-#pragma unroll 4
-            for (u32 cc = 0; cc < 8; cc++) {
-                const uint4 v = *reinterpret_cast<const uint4*>(rp + ((cc ^ sw) << 4));
+            if (need_qnorm) {  // first panel only: the |b| chains run next to the dot chains
+#pragma unroll 2
+                for (u32 cc = 0; cc < 8; cc++) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(rp + ((cc ^ sw) << 4));
 #pragma unroll
-                for (int b = 0; b < QB; b++) {
-                    const float4 qa = sq[(q0i + 2 * cc) * QB + b], qb2 = sq[(q0i + 2 * cc + 1) * QB + b];
-                    acc[b] = dot8_seq_bf16(acc[b], v, qa, qb2);
-                    if (need_qnorm) qsq[b] = sq4_seq(sq4_seq(qsq[b], qa), qb2);
+                    for (int b = 0; b < QB; b++) {
+                        const float4 qa = sq[(q0i + 2 * cc) * QB + b], qb2 = sq[(q0i + 2 * cc + 1) * QB + b];
+                        acc[b] = dot8_seq_bf16(acc[b], v, qa, qb2);
+                        qsq[b] = sq4_seq(sq4_seq(qsq[b], qa), qb2);
+                    }
+                }
+            } else {
+                // steady state: the whole 64-column block unrolled -- the eight swizzled chunk
+                // addresses are loop-invariant per lane and the query offsets immediates
+#pragma unroll
+                for (u32 cc = 0; cc < 8; cc++) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(rp + ((cc ^ sw) << 4));
+#pragma unroll
+                    for (int b = 0; b < QB; b++) {
+                        const float4 qa = sq[(q0i + 2 * cc) * QB + b], qb2 = sq[(q0i + 2 * cc + 1) * QB + b];
+                        acc[b] = dot8_seq_bf16(acc[b], v, qa, qb2);
+                    }
                 }
             }
             if (maybe_mask) {
@@ -985,7 +1046,7 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
             }
         }
         __syncwarp();  // every lane has consumed this stage: hand it back to the copy engine
-        if (lane == 0 && ic < n_chunks) issue();
+        issue();
 
         if (++ci == cpp) {
             if (need_qnorm) {
@@ -1005,7 +1066,8 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
                 top[b].offer(key, lane);
             }
             ci = 0;
-            panel += total_warps;
+            // dynamic deal: the request cursor is exactly one panel ahead by now (or past the end)
+            panel = dyn ? ipanel : panel + total_warps;
         }
         if (++stage == S) {
             stage = 0;
@@ -1013,11 +1075,14 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
         }
     }
     BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 4);
+#ifdef BSR_TC_TIMELINE
+    if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[13] = (unsigned long long)clock64();
+#endif
 #pragma unroll
     for (int b = 0; b < QB; b++) top[b].finish(lane);
     __syncthreads();
     BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 5);
-    scan_epilogue<W, QB>(lists, K, a.k, a.cta_keys, a.fin, a.fuse_final != 0);
+    scan_epilogue<W, QB>(lists, K, a.k, a.cta_keys, a.fin, a.fuse_final != 0, ba.panel_ticket);
 }
 
 #ifndef BSR_TEMPLATES_ONLY  // the plain (non-template) kernels are compiled once, in bsr_api.cu

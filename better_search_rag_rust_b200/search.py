@@ -22,7 +22,7 @@ import numpy as np
 from . import _lib
 from ._lib import BsrError
 from .load_balance import interval_by_rank
-from .vectorstore import GpuVectorstore, _read_parquet_rows
+from .vectorstore import GpuVectorstore, ParquetRowSource, _read_parquet_rows, rank_file_paths
 
 ROOT = 0  # src/mpi_helpers/mod.rs
 KEY_MAX = np.uint64(0xFFFFFFFFFFFFFFFF)
@@ -227,32 +227,57 @@ def _default_device(rank: int) -> int:
     return rank % n.value
 
 
-def open_shard(vstore_dir, rank: int, size: int, *, device: Optional[int] = None) -> CudaShardEngine:
-    """Rank `rank` of `size`'s row block of <vstore_dir>/global.parquet, resident in HBM.
+def open_shard(vstore_dir, rank: int, size: int, *, device: Optional[int] = None,
+               source: str = "global", n_files: Optional[int] = None, dtype: str = "f32") -> CudaShardEngine:
+    """Rank `rank` of `size`'s row block of the store under `vstore_dir`, resident in HBM.
 
-    get_global_vstore + get_count + interval_by_rank + get_many of metrics.rs:23-33, done once;
-    the shard is reloaded when the file changes."""
-    path = os.path.join(os.fspath(vstore_dir), "global.parquet")
+    get_global_vstore + get_count + interval_by_rank + get_many of metrics.rs:23-33, done once; the
+    shard is reloaded when a file changes.  Only the Parquet row groups that overlap the rank's
+    block are decoded (the footers give the row counts), one at a time, and uploaded through the
+    library's pinned double-buffered pipeline -- host memory is bounded by one row group where the
+    reference holds the whole store on every rank.
+
+    source = "global": <dir>/global.parquet (what the reference searches).
+    source = "ranks" : the ingest output <dir>/rank_0.parquet ... rank_{n_files-1}.parquet taken in
+      merge order (tasks.rs:186-197), i.e. the same rows global.parquet would hold, without needing
+      the merged file to exist."""
+    d = os.fspath(vstore_dir)
+    if source == "global":
+        paths = [os.path.join(d, "global.parquet")]
+        if not os.path.exists(paths[0]):
+            _read_parquet_rows(paths[0])  # read_parquet creates a missing file, empty (polars.rs:64-73)
+    elif source == "ranks":
+        paths = rank_file_paths(d, n_files)
+        if not paths:
+            raise FileNotFoundError(f"no rank_*.parquet under {d}")
+    else:
+        raise ValueError("source must be 'global' or 'ranks'")
     device = _default_device(rank) if device is None else device
-    key = (os.path.abspath(path), rank, size, device)
-    st = os.stat(path) if os.path.exists(path) else None
-    stamp = (st.st_mtime_ns, st.st_size) if st else None
+    key = (tuple(os.path.abspath(p) for p in paths), rank, size, device, dtype)
+
+    def stamp_of():
+        return tuple((os.stat(p).st_mtime_ns, os.stat(p).st_size) for p in paths)
+
+    stamp = stamp_of()
     hit = _RESIDENT.get(key)
     if hit and hit[0] == stamp:
         return hit[1]
-    rows = _read_parquet_rows(path)
-    count = rows.shape[0]
-    first, n = interval_by_rank(rank, size, count).rows(count)
-    start = interval_by_rank(rank, size, count).start_index
-    store = GpuVectorstore(None, True, device=device, row_base=min(start, 0xFFFFFFFE),
-                           dim=rows.shape[1] if rows.shape[1] else None, capacity_rows=n)
-    if n:
-        store.append_many(rows[first:first + n])
+    src = ParquetRowSource(paths)
+    count = src.count
+    iv = interval_by_rank(rank, size, count)
+    first, n = iv.rows(count)
+    store = None
+    for block in src.blocks(first, n):
+        if store is None:
+            store = GpuVectorstore(None, True, device=device, row_base=min(iv.start_index, 0xFFFFFFFE),
+                                   dim=block.shape[1], capacity_rows=n, dtype=dtype)
+        store.append_many(block)
+    if store is None:  # empty block (more ranks than rows, or an empty store)
+        store = GpuVectorstore(None, True, device=device, row_base=min(iv.start_index, 0xFFFFFFFE), dtype=dtype)
     eng = CudaShardEngine(store)
     if hit:
         hit[1].store.close()
-    st = os.stat(path)
-    _RESIDENT[key] = ((st.st_mtime_ns, st.st_size), eng)
+    _RESIDENT[key] = (stamp_of(), eng)
     return eng
 
 

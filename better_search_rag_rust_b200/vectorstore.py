@@ -57,28 +57,108 @@ def _read_parquet_rows(path: str) -> np.ndarray:
         _write_parquet_rows(path, np.zeros((0, 0), dtype=np.float32))
         return np.zeros((0, 0), dtype=np.float32)
     table = pq.read_table(path, columns=[EMBEDDINGS_COLUMN])
-    col = table.column(EMBEDDINGS_COLUMN).combine_chunks()
+    return _decode_embeddings(table.column(EMBEDDINGS_COLUMN), path)
+
+
+def _decode_embeddings(col, where: str) -> np.ndarray:
+    """One Arrow `embeddings` array (list / large_list / fixed_size_list of float) -> [n, dim] f32."""
+    import pyarrow as pa
+
     if isinstance(col, pa.ChunkedArray):
-        col = col.chunk(0) if col.num_chunks else pa.array([], type=pa.list_(pa.float32()))
+        col = col.combine_chunks()
+        if isinstance(col, pa.ChunkedArray):
+            col = col.chunk(0) if col.num_chunks else pa.array([], type=pa.list_(pa.float32()))
     if len(col) == 0:
         return np.zeros((0, 0), dtype=np.float32)
     if col.null_count:
         col = col.drop_null()  # get_many's filter_map drops null rows (polars.rs:142)
     if pa.types.is_fixed_size_list(col.type):
         dim = col.type.list_size
-        flat = col.flatten()
     else:
-        offsets = np.asarray(col.offsets)
-        lens = np.diff(offsets)
+        lens = np.diff(np.asarray(col.offsets))
         if len(lens) and not np.all(lens == lens[0]):
-            raise ValueError(f"{path}: embeddings rows have different lengths")
+            raise ValueError(f"{where}: embeddings rows have different lengths")
         dim = int(lens[0]) if len(lens) else 0
-        flat = col.flatten()
-    values = np.asarray(flat.cast(pa.float32()).to_numpy(zero_copy_only=False), dtype=np.float32)
+    values = np.asarray(col.flatten().cast(pa.float32()).to_numpy(zero_copy_only=False), dtype=np.float32)
     return np.ascontiguousarray(values.reshape(len(col), dim))
 
 
-def _write_parquet_rows(path: str, rows: np.ndarray) -> None:
+class ParquetRowSource:
+    """Row-addressable view of one or several Parquet files holding the `embeddings` column, decoded
+    one ROW GROUP at a time.
+
+    The reference decodes the whole of global.parquet on every rank for every search
+    (src/mpi_helpers/metrics.rs:23) -- 307 GB of host memory per rank at 100 M x 768.  Here a rank
+    reads the footers (row counts per row group, no data) and then only the row groups that overlap
+    its row block; host memory is bounded by one row group.
+
+    Several files are the concatenation in list order: for `rank_{r}.parquet` files that is the order
+    merge_vector_stores appends them to the global store (src/mpi_helpers/tasks.rs:186-197), so row g
+    of the concatenation is row g of the global.parquet the reference would have written."""
+
+    def __init__(self, paths: Sequence[str]):
+        import pyarrow.parquet as pq
+
+        self.paths = [os.fspath(p) for p in paths]
+        self._groups = []  # (file index, row group, first global row, rows)
+        self._files = []
+        self.has_nulls = False
+        at = 0
+        for fi, path in enumerate(self.paths):
+            pf = pq.ParquetFile(path)
+            self._files.append(pf)
+            md = pf.metadata
+            if EMBEDDINGS_COLUMN not in pf.schema_arrow.names and md.num_rows:
+                raise ValueError(f"{path}: no `{EMBEDDINGS_COLUMN}` column")
+            for rg in range(md.num_row_groups):
+                g = md.row_group(rg)
+                for ci in range(g.num_columns):
+                    st = g.column(ci).statistics
+                    if g.column(ci).path_in_schema.split(".")[0] == EMBEDDINGS_COLUMN and st is not None \
+                            and st.has_null_count and st.null_count:
+                        self.has_nulls = True
+                self._groups.append((fi, rg, at, g.num_rows))
+                at += g.num_rows
+        self.count = at
+
+    def blocks(self, first: int, n: int):
+        """Yield [m, dim] f32 arrays covering rows [first, first + n) in order."""
+        if self.has_nulls:
+            # null rows are dropped by get_many (polars.rs:142), which shifts every later index: the
+            # row-group arithmetic above does not hold, fall back to the reference's whole-file decode
+            rows = np.concatenate([r for r in (_read_parquet_rows(p) for p in self.paths) if r.shape[0]] or
+                                  [np.zeros((0, 0), np.float32)])
+            if n:
+                yield rows[first:first + n]
+            return
+        end = first + n
+        for fi, rg, at, m in self._groups:
+            if at + m <= first or at >= end or m == 0:
+                continue
+            tbl = self._files[fi].read_row_group(rg, columns=[EMBEDDINGS_COLUMN])
+            rows = _decode_embeddings(tbl.column(EMBEDDINGS_COLUMN), self.paths[fi])
+            if rows.shape[0] != m:  # nulls the footer statistics did not announce
+                raise ValueError(f"{self.paths[fi]}: row group {rg} holds null embeddings; "
+                                 "re-write the file without nulls or load it with get_many")
+            lo, hi = max(first, at) - at, min(end, at + m) - at
+            yield rows[lo:hi]
+
+
+def rank_file_paths(vstore_dir, n_files: Optional[int] = None) -> List[str]:
+    """<dir>/rank_0.parquet, rank_1.parquet, ... (get_local_vstore, src/mpi_helpers/vectorstore.rs:5-13):
+    `n_files` of them, or as many consecutive ones as exist."""
+    d = os.fspath(vstore_dir)
+    if n_files is not None:
+        return [os.path.join(d, f"rank_{r}.parquet") for r in range(n_files)]
+    out = []
+    while os.path.exists(os.path.join(d, f"rank_{len(out)}.parquet")):
+        out.append(os.path.join(d, f"rank_{len(out)}.parquet"))
+    return out
+
+
+def _write_parquet_rows(path: str, rows: np.ndarray, row_group_size: int = 512 * 512) -> None:
+    """ParquetWriter with the options of polars.rs:210-216 (polars' defaults: zstd, row groups of
+    512 x 512 rows)."""
     import pyarrow as pa
     import pyarrow.parquet as pq
 
@@ -86,7 +166,8 @@ def _write_parquet_rows(path: str, rows: np.ndarray) -> None:
     flat = pa.array(np.ascontiguousarray(rows, dtype=np.float32).reshape(-1), type=pa.float32())
     offsets = pa.array(np.arange(n + 1, dtype=np.int64) * dim, type=pa.int64())
     col = pa.LargeListArray.from_arrays(offsets, flat)  # polars' List is Arrow large_list
-    pq.write_table(pa.table({EMBEDDINGS_COLUMN: col}), path, compression="zstd")
+    pq.write_table(pa.table({EMBEDDINGS_COLUMN: col}), path, compression="zstd",
+                   row_group_size=max(1, int(row_group_size)))
 
 
 class GpuVectorstore:

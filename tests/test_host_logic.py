@@ -114,3 +114,63 @@ def test_timing_report_format():
         "  Speedup: 1000.00x"]
     assert BenchmarkManager(1).generate_report(None) == ""
     assert m.get("metrics_calculation").throughput() == pytest.approx(2.8)
+
+
+def test_parquet_row_source_reads_only_the_row_groups_it_needs(tmp_path, monkeypatch):
+    """open_shard's loader: footers give the row counts, only the row groups overlapping the rank's
+    block are decoded (the reference decodes the whole file on every rank, metrics.rs:23)."""
+    from better_search_rag_rust_b200 import vectorstore as V
+    rows = np.arange(1000 * 6, dtype=np.float32).reshape(1000, 6)
+    path = str(tmp_path / "global.parquet")
+    V._write_parquet_rows(path, rows, row_group_size=128)           # 8 row groups
+    src = V.ParquetRowSource([path])
+    assert src.count == 1000 and not src.has_nulls
+    reads = []
+    pf = src._files[0]
+    real = pf.read_row_group
+    monkeypatch.setattr(pf, "read_row_group", lambda rg, **kw: (reads.append(rg), real(rg, **kw))[1])
+    for size in (1, 3, 8, 1001):
+        for rank in range(min(size, 9)):
+            iv = bsr.interval_by_rank(rank, size, 1000)
+            first, n = iv.rows(1000)
+            reads.clear()
+            got = list(src.blocks(first, n))
+            cat = np.concatenate(got) if got else np.zeros((0, 6), np.float32)
+            assert np.array_equal(cat, rows[first:first + n])
+            want_groups = sorted({g for g in range(8) if n and g * 128 < first + n and (g + 1) * 128 > first})
+            assert sorted(reads) == want_groups
+    assert list(src.blocks(1000, 0)) == []
+
+
+def test_rank_files_concatenate_in_merge_order(tmp_path):
+    """rank_{r}.parquet taken in rank order are the rows merge_vector_stores writes to global.parquet
+    (tasks.rs:186-197; empty rank files are skipped there and contribute nothing here)."""
+    from better_search_rag_rust_b200 import vectorstore as V
+    rng = np.random.default_rng(2)
+    parts = [rng.uniform(-1, 1, (n, 16)).astype(np.float32) for n in (300, 0, 17, 450)]
+    for r, p in enumerate(parts):
+        V._write_parquet_rows(str(tmp_path / f"rank_{r}.parquet"), p if len(p) else np.zeros((0, 0), np.float32),
+                              row_group_size=100)
+    glob = np.concatenate([p for p in parts if len(p)])
+    assert [os.path.basename(p) for p in bsr.rank_file_paths(tmp_path)] == [f"rank_{r}.parquet" for r in range(4)]
+    src = V.ParquetRowSource(bsr.rank_file_paths(tmp_path))
+    assert src.count == len(glob)
+    for size in (1, 2, 5):
+        for rank in range(size):
+            first, n = bsr.interval_by_rank(rank, size, len(glob)).rows(len(glob))
+            cat = np.concatenate(list(src.blocks(first, n)) or [np.zeros((0, 16), np.float32)])
+            assert np.array_equal(cat, glob[first:first + n])
+
+
+def test_parquet_row_source_with_null_rows_falls_back_to_whole_file_semantics(tmp_path):
+    """get_many drops null rows (polars.rs:142), so indices are positions among the non-null rows."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    from better_search_rag_rust_b200 import vectorstore as V
+    vals = [[1.0, 2.0], None, [3.0, 4.0], [5.0, 6.0], None, [7.0, 8.0]]
+    path = str(tmp_path / "global.parquet")
+    pq.write_table(pa.table({"embeddings": pa.array(vals, type=pa.large_list(pa.float32()))}), path, row_group_size=2)
+    src = V.ParquetRowSource([path])
+    assert src.has_nulls
+    got = np.concatenate(list(src.blocks(1, 2)))
+    assert got.tolist() == [[3.0, 4.0], [5.0, 6.0]]
