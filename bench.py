@@ -358,11 +358,10 @@ def run_b200(args):
         merged = torch.empty((1, slots), dtype=torch.int64, device=dev)
 
         def step_device():
-            eng.search_candidates(q_dev, k, out=cand)
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, cand)
-                if rank == 0:
-                    eng.merge(gathered, k, out=merged)
+            if world == 1:
+                eng.search_candidates(q_dev, k, out=cand)      # bsr_search_device
+            else:
+                comm.search_device(eng, q_dev, k, out=merged)  # bsr_search_parallel_device (asynchronous)
 
         def step_e2e():
             if world == 1:
@@ -398,7 +397,12 @@ def run_b200(args):
         fence()
         e2e_s = reduce_ranks(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
 
-        out = {"n": n, "steps": n_steps, "ms_dev": ms_dev, "launches": launches, "scan_ms": scan_ms,
+        exchange = "none (one rank)"
+        if world > 1:
+            exchange = ("NVLink mailbox: peer stores from each scan's last CTA into root's HBM, folded in by root's "
+                        "last CTA (one kernel per rank and query)" if comm.uses_mailbox() and args.exchange != "nccl"
+                        else "ncclAllGather of the candidate slots + merge launch on root")
+        out = {"exchange": exchange, "n": n, "steps": n_steps, "ms_dev": ms_dev, "launches": launches, "scan_ms": scan_ms,
                "n_scans": n_scans, "e2e_s": e2e_s, "scan_bytes": store.scan_bytes(),
                "t_wall": (t_wall0, t_wall1), "parity": "skipped (--no-parity)"}
 
@@ -421,6 +425,10 @@ def run_b200(args):
                 gd = np.concatenate([p[1] for p in lists])
                 fi, fd = co.compute_global_top_k(gi, gd, k)            # metrics.rs:141-171
                 idx, dst, cnt = res
+                if world > 1:  # the device-resident leg's last result, too
+                    mi, md, mc = eng.unpack(merged, k)
+                    ok_local = ok_local and (int(mc[0]) == len(fi) and mi[0, :mc[0]].tolist() == fi.tolist()
+                                             and md[0, :mc[0]].view(np.uint32).tolist() == fd.view(np.uint32).tolist())
                 ok_global = (int(cnt[0]) == len(fi) and idx[0, :cnt[0]].tolist() == fi.tolist()
                              and dst[0, :cnt[0]].view(np.uint32).tolist() == fd.view(np.uint32).tolist()
                              # the self-query comes back first with distance exactly 0 (src/main.rs:148-154)
@@ -479,7 +487,7 @@ def run_b200(args):
                     "ms_per_step": m["e2e_s"] / m["steps"] * 1e3,
                     "path": "bsr_search (C ABI, host buffers)" if world == 1 else
                             "bsr_search_parallel (C ABI, host buffers: scan -> candidate exchange -> merge on root)"},
-            "gpu_launches": int(m["launches"]),
+            "gpu_launches": int(m["launches"]), "exchange": m["exchange"],
             "parity_checked": m["parity"], "parity_detail": m.get("parity_detail"),
         }
 
@@ -492,6 +500,7 @@ def run_b200(args):
         "queries_per_s_whole_store": sm["queries_per_s_whole_store"],
         "wall_ms_per_step": (main["t_wall"][1] - main["t_wall"][0]) / steps * 1e3,
         "roofline": sm["roofline"], "e2e": sm["e2e"], "gpu_launches": sm["gpu_launches"],
+        "exchange": sm["exchange"],
         "parity_checked": sm["parity_checked"], "parity_detail": sm["parity_detail"],
         "clocks": sampler.summary(*main["t_wall"]),
     }

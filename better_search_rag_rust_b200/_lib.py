@@ -77,6 +77,9 @@ SIGNATURES = {
     "bsr_comm_destroy": (C.c_int, [C.c_void_p]),
     "bsr_search_parallel": (C.c_int, [_store, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    "bsr_search_parallel_device": (C.c_int, [_store, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p,
+                                             C.c_void_p]),
+    "bsr_comm_uses_mailbox": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "bsr_store_set_tensor_min_batch": (C.c_int, [_store, C.c_uint32]),
     "bsr_store_set_option": (C.c_int, [_store, C.c_char_p, C.c_int64]),
     "bsr_store_launch_count": (C.c_int, [_store, _u64p]),

@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -77,6 +78,7 @@ struct Knobs {
     int tc_stats = 0;        // BSR_TC_STATS
     int wide = -1;           // BSR_WIDE: 16-warp CTAs: -1 auto (small f32 stores, every bf16 store), 0 never, 1 always
     int no_tickets = 0;      // BSR_NO_TICKETS: static panel deal on large stores too
+    int no_param_query = 0;  // BSR_NO_PARAM_QUERY: bsr_search always copies the query and waits on the stream
     int no_pdl = 0;          // BSR_NO_PDL: plain stream-ordered launches for back-to-back scans
     int no_mailbox = 0;      // BSR_NO_MAILBOX: cross-rank exchange through ncclAllGather only
 };
@@ -101,6 +103,7 @@ static const Knobs& knobs() {
         v.tc_stats = getenv("BSR_TC_STATS") != nullptr;
         v.wide = geti("BSR_WIDE", -1);
         v.no_tickets = getenv("BSR_NO_TICKETS") != nullptr;
+        v.no_param_query = getenv("BSR_NO_PARAM_QUERY") != nullptr;
         v.no_pdl = getenv("BSR_NO_PDL") != nullptr;
         v.no_mailbox = getenv("BSR_NO_MAILBOX") != nullptr;
         return v;
@@ -143,6 +146,13 @@ struct bsr_store {
     void* h_stage[2] = {nullptr, nullptr};
     size_t h_stage_bytes = 0;
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+
+    // set by bsr_search around ONE search_device_impl call: the host query to pass in the kernel's
+    // parameter block, and the pinned-host flag the last CTA publishes behind the results
+    const float* param_query = nullptr;
+    u32* host_flag = nullptr;
+    u32 flag_seq = 0;
+    const Mailbox* mailbox = nullptr;  // set by bsr_search_parallel around one fused launch
 
     u64 launches = 0;
     // All calls on a handle share one scratch set (cta_keys, merge buffers, the last-CTA ticket).  The
@@ -587,6 +597,19 @@ static int launch_scan(bsr_store* s, const ScanArgs& a, unsigned grid, size_t sm
     return BSR_OK;
 }
 
+// |b| of a host query exactly as the reference computes it (src/metrics.rs:155,159): a left-to-right
+// binary32 fold of separately rounded squares, then sqrt.  `volatile` keeps every intermediate a
+// binary32 value and the multiply and the add two operations whatever the host compiler's
+// contraction / excess-precision settings are.
+static float host_query_magnitude(const float* q, u32 dim) {
+    volatile float acc = 0.0f;
+    for (u32 i = 0; i < dim; i++) {
+        volatile float sq = q[i] * q[i];
+        acc = acc + sq;
+    }
+    return sqrtf(acc);
+}
+
 static const size_t kProfPairs = 1024;
 
 static int prof_fold(bsr_store* s) {
@@ -669,6 +692,12 @@ static int launch_scan_bulk_t(bsr_store* s, const ScanArgs& a, unsigned grid, u3
     ba.active_warps = active_warps;
     ba.interleave = 1u;  // panels dealt over CTAs first: the ring is sized for active_warps on that assumption
     ba.panel_ticket = panel_ticket;
+    ba.query_in_params = 0;
+    if (QB == 1 && s->param_query) {  // single host query: rides in the parameter block (no H2D copy)
+        ba.query_in_params = 1;
+        memcpy(ba.qparam, s->param_query, (size_t)s->dim * sizeof(float));
+        ba.qparam_mag = host_query_magnitude(s->param_query, s->dim);
+    }
     scan_topk_bulk_kernel<QB, BF16, W>
         <<<grid, W * 32, bulk_smem_bytes(s, a.k_pad, stages, QB, active_warps, W), st>>>(ba);
     s->launches++;
@@ -976,6 +1005,10 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
         a.fin.idx = d_idx ? d_idx + (size_t)q * k : nullptr;
         a.fin.dist = d_idx ? d_dist + (size_t)q * k : nullptr;
         a.fin.count = d_idx ? d_count + q : nullptr;
+        a.fin.host_flag = (fuse && nq == 1) ? s->host_flag : nullptr;
+        a.fin.flag_value = s->flag_seq;
+        a.fin.mb = Mailbox{};
+        if (s->mailbox && K == 32 && nq == 1) a.fin.mb = *s->mailbox;
         a.dbg = a.fin.dbg = nullptr;
 #ifdef BSR_TC_TIMELINE
         static unsigned long long* d_dbg = nullptr;
@@ -1109,6 +1142,26 @@ extern "C" int bsr_unpack_device(bsr_store* s, const uint64_t* d_cand, uint32_t 
     return mark_busy(s, st);
 }
 
+// Host side of FinalOut::host_flag: wait until the last CTA has published `seq` behind the results.
+// Polls the pinned word; every ~20 us also asks the stream, so a failed launch or a faulting kernel
+// surfaces as an error instead of a hang.
+static int wait_host_flag(bsr_store* s, const volatile u32* flag, u32 seq) {
+    for (u32 spins = 0;; spins++) {
+        if (*flag == seq) return BSR_OK;
+        if ((spins & 0x3FF) == 0x3FF) {
+            cudaError_t e = cudaStreamQuery(s->stream);
+            if (e == cudaSuccess) {
+                if (*flag == seq) return BSR_OK;
+                return fail(BSR_ERR_CUDA, "bsr_search: the scan finished without publishing its result");
+            }
+            if (e != cudaErrorNotReady) return fail(BSR_ERR_CUDA, "bsr_search: %s", cudaGetErrorString(e));
+        }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+}
+
 extern "C" int bsr_search(bsr_store* s, const float* queries, uint32_t nq, uint32_t k,
                           uint64_t* out_idx, float* out_dist, uint32_t* out_count) {
     TRY(check_search_args(s, queries, nq, k, "bsr_search"));
@@ -1119,32 +1172,55 @@ extern "C" int bsr_search(bsr_store* s, const float* queries, uint32_t nq, uint3
     const size_t qbytes = (size_t)nq * s->dim * sizeof(float);
     const size_t ibytes = (size_t)nq * k * sizeof(u64), dbytes = (size_t)nq * k * sizeof(float),
                  cbytes = (size_t)nq * sizeof(u32);
-    // one packed result block [idx | dist | count] on the device and in pinned host memory, so a
-    // search is one H2D copy, the kernels, one D2H copy
+    // one packed result block [idx | dist | count | flag] on the device and in pinned host memory, so a
+    // search is at most one H2D copy, the kernels, one D2H copy
     const size_t rbytes = ibytes + dbytes + cbytes;
     const size_t off_r = (qbytes + 15) & ~(size_t)15;
-    TRY(ensure_pinned(s, off_r + rbytes));
+    const size_t off_flag = (off_r + rbytes + 63) & ~(size_t)63;
+    TRY(ensure_pinned(s, off_flag + 64));
     TRY(ensure(s->d_queries, qbytes));
     TRY(ensure(s->d_cand, (size_t)nq * K * sizeof(u64)));
     TRY(ensure(s->d_result, rbytes));
     char* h = (char*)s->h_pinned;
-    memcpy(h, queries, qbytes);
     if (s->n_rows == 0) {
         // empty shard: compute_local_top_k returns an empty list (metrics.rs:36-52)
         memset(out_count, 0, cbytes);
         return BSR_OK;
     }
     TRY(order_after_previous(s, s->stream));
-    CU(cudaMemcpyAsync(s->d_queries.p, h, qbytes, cudaMemcpyHostToDevice, s->stream));
     // Small results (a few queries): the kernel that unpacks writes them straight into the pinned
     // host block (mapped into the device's address space under UVA) -- the D2H transfer still
     // happens every call, as posted PCIe writes instead of a separate copy operation.
     const bool direct = rbytes <= kDirectResultBytes;
+    // One query, one fused launch (k <= 128, bulk kernel, not the tensor path): the query travels in the
+    // kernel's parameter block -- the H2D transfer of its 4*dim bytes is part of the launch -- and
+    // the host waits on a flag the last CTA writes behind the results, not on the stream.
+    const bool one_launch = direct && nq == 1 && K <= 128 && !s->kn.no_fuse_wide && !s->kn.scan_ldg &&
+                            s->dim <= kParamQueryMax && !s->kn.no_param_query && bulk_stages(s, K, 1) >= 2 &&
+                            !tensor_eligible(s, 1, K);
     char* r = direct ? h + off_r : (char*)s->d_result.p;
-    TRY(search_device_impl(s, (const float*)s->d_queries.p, nq, k, (u64*)s->d_cand.p, (u64*)r,
-                           (float*)(r + ibytes), (u32*)(r + ibytes + dbytes), s->stream));
-    if (!direct) CU(cudaMemcpyAsync(h + off_r, r, rbytes, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
+    volatile u32* flag = (volatile u32*)(h + off_flag);
+    if (one_launch) {
+        s->param_query = queries;
+        s->host_flag = (u32*)flag;
+        s->flag_seq = s->flag_seq + 1 ? s->flag_seq + 1 : 1;  // never 0
+        *flag = 0;  // whatever an earlier call left in this word of the shared pinned block
+    } else {
+        memcpy(h, queries, qbytes);
+        CU(cudaMemcpyAsync(s->d_queries.p, h, qbytes, cudaMemcpyHostToDevice, s->stream));
+    }
+    int rc = search_device_impl(s, (const float*)s->d_queries.p, nq, k, (u64*)s->d_cand.p, (u64*)r,
+                                (float*)(r + ibytes), (u32*)(r + ibytes + dbytes), s->stream);
+    s->param_query = nullptr;
+    s->host_flag = nullptr;
+    TRY(rc);
+    if (one_launch) {
+        TRY(wait_host_flag(s, flag, s->flag_seq));
+        // the kernel may still be retiring; the next call on this handle is stream-ordered behind it
+    } else {
+        if (!direct) CU(cudaMemcpyAsync(h + off_r, r, rbytes, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
     mark_idle(s);
     memcpy(out_idx, h + off_r, ibytes);
     memcpy(out_dist, h + off_r + ibytes, dbytes);
@@ -1286,7 +1362,22 @@ NcclApi& nccl() {
 struct bsr_comm {
     void* comm = nullptr;
     int n_ranks = 0, rank = 0, device = 0;
+    // NVLink mailbox (see Mailbox in bsr_kernels.cuh): every rank owns one device block
+    // [mailbox entries | ack word]; root reads its own entries and writes the peers' ack words, the
+    // peers write root's entries.  Mapped across processes with CUDA IPC at bsr_comm_create.
+    bool mb_ok = false;
+    void* mb_local = nullptr;                // my block (cudaMalloc)
+    void* mb_root = nullptr;                 // non-root: root's block, mapped into this process
+    std::vector<void*> mb_peers;             // root: every peer's block (index = rank; [0] unused)
+    void* d_ack_ptrs = nullptr;              // root: device array of the peers' ack-word addresses
+    u32* h_status = nullptr;                 // pinned: set to 1 by a kernel that gave up waiting
+    u32 seq = 0;                             // sequence number of the last mailbox search
+    cudaStream_t stream = nullptr;
 };
+
+static size_t mailbox_entries_bytes(int n_ranks) {
+    return (size_t)kMbDepth * n_ranks * kMbSlots * sizeof(ulonglong2);
+}
 
 #define NCCL(expr)                                                                              \
     do {                                                                                        \
@@ -1302,6 +1393,82 @@ extern "C" int bsr_comm_unique_id(uint8_t id[BSR_COMM_ID_BYTES]) {
     NcclId nid;
     NCCL(nccl().GetUniqueId(&nid));
     memcpy(id, nid.internal, BSR_COMM_ID_BYTES);
+    return BSR_OK;
+}
+
+// What every rank tells the others at bsr_comm_create (one all-gather of this record).
+struct MailboxHello {
+    cudaIpcMemHandle_t handle;  // of mb_local
+    char uuid[16];              // the GPU: two ranks on one GPU must not wait on each other inside kernels
+    int ok;                     // local allocation + handle export worked
+    int pad[3];
+};
+
+// Collective.  Any failure simply leaves mb_ok false on EVERY rank (they all look at the same gathered
+// records and exchange their mapping results), and searches use ncclAllGather.
+static int mailbox_setup(bsr_comm* c) {
+    c->mb_ok = false;
+    if (c->n_ranks < 2 || c->n_ranks > 32 || getenv("BSR_NO_MAILBOX")) return BSR_OK;  // decided identically everywhere
+    const size_t ebytes = mailbox_entries_bytes(c->n_ranks), bytes = ebytes + 256;
+    MailboxHello me;
+    memset(&me, 0, sizeof me);
+    cudaDeviceProp prop;
+    bool ok = cudaGetDeviceProperties(&prop, c->device) == cudaSuccess;
+    if (ok) memcpy(me.uuid, &prop.uuid, 16);
+    ok = ok && cudaMalloc(&c->mb_local, bytes) == cudaSuccess;
+    ok = ok && cudaMemset(c->mb_local, 0, bytes) == cudaSuccess;
+    ok = ok && cudaIpcGetMemHandle(&me.handle, c->mb_local) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&c->h_status, 64) == cudaSuccess;
+    if (c->h_status) *c->h_status = 0;
+    cudaGetLastError();
+    me.ok = ok ? 1 : 0;
+    // gather the records (device staging: NCCL moves device memory)
+    MailboxHello* d_all = nullptr;
+    std::vector<MailboxHello> all((size_t)c->n_ranks);
+    CU(cudaMalloc((void**)&d_all, sizeof(MailboxHello) * (c->n_ranks + 1)));
+    CU(cudaMemcpyAsync(d_all + c->n_ranks, &me, sizeof me, cudaMemcpyHostToDevice, c->stream));
+    NCCL(nccl().AllGather(d_all + c->n_ranks, d_all, sizeof(MailboxHello), 0 /* ncclInt8 */, c->comm, c->stream));
+    CU(cudaMemcpyAsync(all.data(), d_all, sizeof(MailboxHello) * c->n_ranks, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    bool all_ok = true;
+    for (int r = 0; r < c->n_ranks; r++) {
+        all_ok = all_ok && all[r].ok;
+        for (int q = 0; q < r; q++) all_ok = all_ok && memcmp(all[r].uuid, all[q].uuid, 16) != 0;
+    }
+    // map: peers -> root's block; root -> every peer's block
+    int mapped = all_ok ? 1 : 0;
+    if (all_ok) {
+        if (c->rank == 0) {
+            c->mb_peers.assign((size_t)c->n_ranks, nullptr);
+            std::vector<u32*> acks((size_t)c->n_ranks, nullptr);
+            for (int r = 1; r < c->n_ranks && mapped; r++) {
+                if (cudaIpcOpenMemHandle(&c->mb_peers[r], all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    c->mb_peers[r] = nullptr;
+                    mapped = 0;
+                } else {
+                    acks[r] = (u32*)((char*)c->mb_peers[r] + ebytes);
+                }
+            }
+            if (mapped && (cudaMalloc(&c->d_ack_ptrs, sizeof(u32*) * c->n_ranks) != cudaSuccess ||
+                           cudaMemcpy(c->d_ack_ptrs, acks.data(), sizeof(u32*) * c->n_ranks, cudaMemcpyHostToDevice) != cudaSuccess))
+                mapped = 0;
+        } else if (cudaIpcOpenMemHandle(&c->mb_root, all[0].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            c->mb_root = nullptr;
+            mapped = 0;
+        }
+        cudaGetLastError();
+    }
+    // everyone must have succeeded
+    int* d_flags = (int*)d_all;
+    CU(cudaMemcpyAsync(d_flags + c->n_ranks, &mapped, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    NCCL(nccl().AllGather(d_flags + c->n_ranks, d_flags, sizeof(int), 0, c->comm, c->stream));
+    std::vector<int> flags((size_t)c->n_ranks);
+    CU(cudaMemcpyAsync(flags.data(), d_flags, sizeof(int) * c->n_ranks, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(d_all));
+    bool every = true;
+    for (int f : flags) every = every && f;
+    c->mb_ok = every;
     return BSR_OK;
 }
 
@@ -1325,6 +1492,16 @@ extern "C" int bsr_comm_create(const uint8_t id[BSR_COMM_ID_BYTES], int n_ranks,
         return fail(BSR_ERR_CUDA, "ncclCommInitRank failed: %s",
                     nccl().GetErrorString ? nccl().GetErrorString(r) : "NCCL error");
     }
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        nccl().CommDestroy(c->comm);
+        delete c;
+        return fail(BSR_ERR_CUDA, "bsr_comm_create: cudaStreamCreate failed");
+    }
+    int rc = mailbox_setup(c);
+    if (rc != BSR_OK) {
+        bsr_comm_destroy(c);
+        return rc;
+    }
     *out = c;
     return BSR_OK;
 }
@@ -1332,8 +1509,70 @@ extern "C" int bsr_comm_create(const uint8_t id[BSR_COMM_ID_BYTES], int n_ranks,
 extern "C" int bsr_comm_destroy(bsr_comm* c) {
     if (!c) return BSR_OK;
     DeviceGuard g(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (void* p : c->mb_peers)
+        if (p) cudaIpcCloseMemHandle(p);
+    if (c->mb_root) cudaIpcCloseMemHandle(c->mb_root);
+    if (c->d_ack_ptrs) cudaFree(c->d_ack_ptrs);
+    if (c->mb_local) cudaFree(c->mb_local);
+    if (c->h_status) cudaFreeHost(c->h_status);
     if (c->comm) nccl().CommDestroy(c->comm);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
+    return BSR_OK;
+}
+
+extern "C" int bsr_comm_uses_mailbox(const bsr_comm* c, int* yes) {
+    CHECK(c && yes, BSR_ERR_INVALID, "bsr_comm_uses_mailbox: null argument");
+    *yes = c->mb_ok ? 1 : 0;
+    return BSR_OK;
+}
+
+// The Mailbox record of search `seq` for this rank.
+static Mailbox mailbox_for(const bsr_comm* c, u32 seq) {
+    Mailbox mb{};
+    const size_t ebytes = mailbox_entries_bytes(c->n_ranks);
+    const size_t slot = (size_t)(seq % kMbDepth) * c->n_ranks * kMbSlots;
+    if (c->rank == 0) {
+        mb.recv = (const ulonglong2*)c->mb_local + slot;
+        mb.ack_remote = (u32* const*)c->d_ack_ptrs;
+    } else {
+        mb.send = (ulonglong2*)c->mb_root + slot + (size_t)c->rank * kMbSlots;
+        mb.ack_local = (const u32*)((const char*)c->mb_local + ebytes);
+    }
+    mb.status = c->h_status;
+    mb.n_ranks = (u32)c->n_ranks;
+    mb.seq = seq;
+    return mb;
+}
+
+// Can this search exchange its candidates through the NVLink mailbox?  Every input is identical on all
+// ranks (arguments, dimension, option), so all ranks take the same path.
+static bool mailbox_usable(const bsr_store* s, const bsr_comm* c, u32 nq, u32 K) {
+    return c->mb_ok && !s->kn.no_mailbox && nq == 1 && K == kMbSlots && !s->kn.scan_ldg &&
+           bulk_stages(s, K, 1) >= 2 && !tensor_eligible(s, 1, K);
+}
+
+static u32 next_mailbox_seq(bsr_comm* c) {
+    c->seq = c->seq + 1 ? c->seq + 1 : 1;  // never 0: a fresh mailbox reads 0
+    return c->seq;
+}
+
+// A rank with nothing to scan (empty shard, or a local failure) still takes part: one warp sends an
+// empty list / folds the peers' lists and publishes.
+static int launch_mailbox_only(bsr_store* s, const Mailbox& mb, u32 k, u64* d_cand, u64* d_idx, float* d_dist,
+                               u32* d_count, u32* host_flag, u32 flag_value, cudaStream_t st) {
+    FinalOut fo{};
+    fo.keys = d_cand;
+    fo.idx = d_idx;
+    fo.dist = d_dist;
+    fo.count = d_count;
+    fo.host_flag = host_flag;
+    fo.flag_value = flag_value;
+    fo.mb = mb;
+    mailbox_only_kernel<<<1, 32, 0, st>>>(fo, k);
+    s->launches++;
+    CU(cudaGetLastError());
     return BSR_OK;
 }
 
@@ -1356,18 +1595,73 @@ extern "C" int bsr_search_parallel(bsr_store* s, bsr_comm* c, const float* queri
     const size_t ibytes = (size_t)nq * k * sizeof(u64), dbytes = (size_t)nq * k * sizeof(float),
                  cbytes = (size_t)nq * sizeof(u32);
     const size_t rbytes = ibytes + dbytes + cbytes, off_r = (qbytes + 15) & ~(size_t)15;
+    const size_t off_flag = (off_r + rbytes + 63) & ~(size_t)63;
     const size_t cand_bytes = (size_t)nq * K * sizeof(u64);
     // the two buffers the exchange itself needs; without them this rank cannot take part at all
     TRY(ensure(s->d_cand, cand_bytes));
     TRY(ensure(s->d_gather, cand_bytes * c->n_ranks + cand_bytes));
+    TRY(ensure_pinned(s, off_flag + 64));
     TRY(order_after_previous(s, s->stream));
+    char* h = (char*)s->h_pinned;
 
-    char* h = nullptr;
+    if (mailbox_usable(s, c, nq, K)) {
+        // ---- one fused launch per rank: scan -> (NVLink stores into root's mailbox | root folds them in) ----
+        const u32 seq = next_mailbox_seq(c);
+        const Mailbox mb = mailbox_for(c, seq);
+        *c->h_status = 0;
+        volatile u32* flag = (volatile u32*)(h + off_flag);
+        *flag = 0;
+        s->flag_seq = s->flag_seq + 1 ? s->flag_seq + 1 : 1;
+        char* r = h + off_r;  // nq == 1: results go straight to the pinned block
+        u64* d_idx = root ? (u64*)r : nullptr;
+        float* d_dist = root ? (float*)(r + ibytes) : nullptr;
+        u32* d_count = root ? (u32*)(r + ibytes + dbytes) : nullptr;
+        int local_rc = BSR_OK;
+        if (s->n_rows != 0) {
+            const bool in_params = s->dim <= kParamQueryMax && !s->kn.no_param_query;
+            if (!in_params) {
+                local_rc = ensure(s->d_queries, qbytes);
+                if (local_rc == BSR_OK) {
+                    memcpy(h, queries, qbytes);
+                    if (cudaMemcpyAsync(s->d_queries.p, h, qbytes, cudaMemcpyHostToDevice, s->stream) != cudaSuccess)
+                        local_rc = fail(BSR_ERR_CUDA, "bsr_search_parallel: query upload failed");
+                }
+            }
+            if (local_rc == BSR_OK) {
+                s->param_query = in_params ? queries : nullptr;
+                s->host_flag = (u32*)flag;
+                s->mailbox = &mb;
+                local_rc = search_device_impl(s, (const float*)s->d_queries.p, nq, k, (u64*)s->d_cand.p, d_idx, d_dist,
+                                              d_count, s->stream);
+                s->param_query = nullptr;
+                s->host_flag = nullptr;
+                s->mailbox = nullptr;
+            }
+        }
+        char local_err[sizeof g_err];
+        if (local_rc != BSR_OK) memcpy(local_err, g_err, sizeof g_err);
+        if (s->n_rows == 0 || local_rc != BSR_OK)
+            TRY(launch_mailbox_only(s, mb, k, (u64*)s->d_cand.p, d_idx, d_dist, d_count, (u32*)flag, s->flag_seq, s->stream));
+        TRY(wait_host_flag(s, flag, s->flag_seq));
+        mark_idle(s);
+        if (local_rc != BSR_OK) {
+            memcpy(g_err, local_err, sizeof g_err);
+            return local_rc;
+        }
+        CHECK(*c->h_status == 0, BSR_ERR_CUDA,
+              "bsr_search_parallel: a rank did not deliver its candidates (mailbox wait gave up)");
+        if (root) {
+            memcpy(out_idx, r, ibytes);
+            memcpy(out_dist, r + ibytes, dbytes);
+            memcpy(out_count, r + ibytes + dbytes, cbytes);
+        }
+        return BSR_OK;
+    }
+
+    // ---- ncclAllGather of the candidate slots + merge launch on root ----
     auto local_scan = [&]() -> int {
-        TRY(ensure_pinned(s, off_r + rbytes));
         TRY(ensure(s->d_queries, qbytes));
         TRY(ensure(s->d_result, rbytes));
-        h = (char*)s->h_pinned;
         memcpy(h, queries, qbytes);
         CU(cudaMemcpyAsync(s->d_queries.p, h, qbytes, cudaMemcpyHostToDevice, s->stream));
         if (s->n_rows == 0) {
@@ -1426,6 +1720,65 @@ extern "C" int bsr_search_parallel(bsr_store* s, bsr_comm* c, const float* queri
         memcpy(out_count, h + off_r + ibytes + dbytes, cbytes);
     }
     return BSR_OK;
+}
+
+// The same collective with device-resident queries and candidates, asynchronous on `stream`: what a
+// host keeps in flight back to back (the mailbox lets a rank run kMbDepth searches ahead of root).
+extern "C" int bsr_search_parallel_device(bsr_store* s, bsr_comm* c, const float* d_queries, uint32_t nq,
+                                          uint32_t k, uint64_t* d_candidates, void* stream) {
+    TRY(check_search_args(s, d_queries, nq, k, "bsr_search_parallel_device"));
+    CHECK(c && c->comm, BSR_ERR_INVALID, "bsr_search_parallel_device: null communicator");
+    CHECK(c->device == s->device, BSR_ERR_INVALID, "bsr_search_parallel_device: shard and communicator are on different devices");
+    if (nq == 0) return BSR_OK;
+    CHECK(d_candidates, BSR_ERR_INVALID, "bsr_search_parallel_device: null output");
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const u32 K = bsr_candidate_slots(k);
+    const size_t cand_bytes = (size_t)nq * K * sizeof(u64);
+    TRY(order_after_previous(s, st));
+    if (mailbox_usable(s, c, nq, K)) {
+        const u32 seq = next_mailbox_seq(c);
+        const Mailbox mb = mailbox_for(c, seq);
+        int rc = BSR_OK;
+        if (s->n_rows != 0) {
+            s->mailbox = &mb;
+            rc = search_device_impl(s, d_queries, nq, k, (u64*)d_candidates, nullptr, nullptr, nullptr, st);
+            s->mailbox = nullptr;
+        }
+        char local_err[sizeof g_err];
+        if (rc != BSR_OK) memcpy(local_err, g_err, sizeof g_err);
+        if (s->n_rows == 0 || rc != BSR_OK)
+            TRY(launch_mailbox_only(s, mb, k, (u64*)d_candidates, nullptr, nullptr, nullptr, nullptr, 0, st));
+        TRY(mark_busy(s, st));
+        if (rc != BSR_OK) memcpy(g_err, local_err, sizeof g_err);
+        return rc;
+    }
+    TRY(ensure(s->d_cand, cand_bytes));
+    TRY(ensure(s->d_gather, cand_bytes * c->n_ranks));
+    int rc = BSR_OK;
+    if (s->n_rows != 0) rc = search_device_impl(s, d_queries, nq, k, (u64*)s->d_cand.p, nullptr, nullptr, nullptr, st);
+    char local_err[sizeof g_err];
+    if (rc != BSR_OK) memcpy(local_err, g_err, sizeof g_err);
+    if (s->n_rows == 0 || rc != BSR_OK) CU(cudaMemsetAsync(s->d_cand.p, 0xFF, cand_bytes, st));
+    NCCL(nccl().AllGather(s->d_cand.p, s->d_gather.p, (size_t)nq * K, kNcclUint64, c->comm, st));
+    if (c->rank == 0) {
+        if (K == 32) {
+            merge32_kernel<<<nq, 32, 0, st>>>((const u64*)s->d_gather.p, (u32)c->n_ranks, (size_t)nq * K, K, k,
+                                              (u64*)d_candidates, nullptr, nullptr, nullptr);
+            s->launches++;
+            CU(cudaGetLastError());
+        } else {
+            const u32 max_per_cta = std::max<u32>(2, kMergeMaxKeys / K);
+            const size_t inter = (size_t)nq * ((c->n_ranks + max_per_cta - 1) / max_per_cta) * K * sizeof(u64);
+            TRY(ensure(s->merge_a, inter));
+            TRY(ensure(s->merge_b, inter));
+            TRY(merge_tree(s, (const u64*)s->d_gather.p, (u32)c->n_ranks, nq, K, k, (size_t)nq * K, K,
+                           (u64*)d_candidates, st));
+        }
+    }
+    TRY(mark_busy(s, st));
+    if (rc != BSR_OK) memcpy(g_err, local_err, sizeof g_err);
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1489,6 +1842,7 @@ extern "C" int bsr_store_set_option(bsr_store* s, const char* name, int64_t valu
         {"tensor_stages", &s->kn.tensor_stages}, {"tensor_stage_kb", &s->kn.tensor_stage_kb},
         {"tc_stats", &s->kn.tc_stats},         {"no_pdl", &s->kn.no_pdl},
         {"wide", &s->kn.wide},                 {"no_tickets", &s->kn.no_tickets},
+        {"no_param_query", &s->kn.no_param_query},
         {"no_mailbox", &s->kn.no_mailbox},
     };
     for (auto& t : table)

@@ -239,6 +239,12 @@ class DeviceWorld {
     int rank() const { return rank_; }
     int size() const { return size_; }
     bsr_comm* handle() const { return c_; }
+    // single-query top_k <= 32 searches go through NVLink peer stores fused into the scan kernel
+    bool uses_mailbox() const {
+        int yes = 0;
+        check(bsr_comm_uses_mailbox(c_, &yes));
+        return yes != 0;
+    }
 
   private:
     bsr_comm* c_ = nullptr;

@@ -67,6 +67,14 @@ __device__ __forceinline__ bool differs(float a, float b) {
 __device__ __forceinline__ bool differs4(const float4& a, const float4& q) {
     return differs(a.x, q.x) || differs(a.y, q.y) || differs(a.z, q.z) || differs(a.w, q.w);
 }
+// Bitwise-equal quads never "differ" (a - a is 0, or NaN for NaN / inf, and neither is > 1e-10): the
+// common case on the one row that IS the query (the reference's self-query) costs three integer ops
+// per quad instead of four subtract-compare pairs.
+__device__ __forceinline__ bool differs4_fast(const float4& a, const float4& q) {
+    const u32 x = (__float_as_uint(a.x) ^ __float_as_uint(q.x)) | (__float_as_uint(a.y) ^ __float_as_uint(q.y)) |
+                  (__float_as_uint(a.z) ^ __float_as_uint(q.z)) | (__float_as_uint(a.w) ^ __float_as_uint(q.w));
+    return x != 0u && differs4(a, q);
+}
 
 // ------------------------------------------------------------------------------------------
 // BF16 stores use a second layout, shared by the exact scan and the tensor-core path: tiles of
@@ -334,8 +342,18 @@ struct WarpTopK {
     }
     __device__ __forceinline__ void finish(int lane) {
         if (cnt < K) {
+            // fill phase not completed: slots [cnt, K) still hold KEY_MAX.  One offer (a single panel, the
+            // small-store case): the 32 keys are sorted in registers; otherwise the filled prefix, rounded
+            // up to a power of two, in shared memory.
             __syncwarp();
-            warp_sort_list(list, K, lane);
+            if (cnt <= 32) {
+                if (cnt) list[lane] = warp_sort32(list[lane], lane);
+                __syncwarp();
+            } else {
+                u32 n2 = 64;
+                while (n2 < cnt) n2 <<= 1;
+                warp_sort_list(list, n2, lane);
+            }
         } else if (pc) {
             flush(lane);
         }
@@ -397,6 +415,91 @@ __device__ __forceinline__ u64 ldcg_u64(const u64* p) {
     return v;
 }
 
+// ------------------------------------------------------------------------------------------
+// Cross-rank candidate exchange over NVLink peer memory ("mailbox"), fused into the scan's last CTA.
+// Replaces gather_top_k_results' messages (src/mpi_helpers/metrics.rs:56-138) and the separate merge
+// launch: every non-root rank stores its shard's 32 candidate slots straight into root's HBM; root's
+// last CTA waits for them, folds them into its own list and writes the final top-k.
+//
+//   entry = 16 bytes {key, seq}, written with ONE 16-byte store: a peer store is delivered whole, so an
+//   entry whose seq field equals the current search's sequence number carries that search's key -- no
+//   fence, no separate flag (the "LL" protocol of collective libraries).
+//   root's mailbox: [kMbDepth][n_ranks][32] entries; search `seq` uses slot seq % kMbDepth, so a peer
+//   may run up to kMbDepth searches ahead of root before it has to wait for root's acknowledgement
+//   (root stores the last sequence number it has consumed into every peer's `ack` word).
+// ------------------------------------------------------------------------------------------
+constexpr u32 kMbDepth = 4;
+constexpr u32 kMbSlots = 32;  // top_k <= 32 (one candidate block per rank)
+
+struct Mailbox {
+    ulonglong2* send;         // non-root: root's entries for (seq % kMbDepth, my rank) -- PEER memory; else nullptr
+    const ulonglong2* recv;   // root: my entries for seq % kMbDepth, [n_ranks][32] -- local memory; else nullptr
+    const u32* ack_local;     // non-root: where root's acknowledgements land (local memory)
+    u32* const* ack_remote;   // root: [n_ranks] pointers to the peers' ack words (PEER memory)
+    u32* status;              // pinned host word, set to 1 when a wait below gave up
+    u32 n_ranks, seq;
+};
+
+__device__ __forceinline__ ulonglong2 ld_volatile_v2(const ulonglong2* p) {
+    ulonglong2 v;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_v2(ulonglong2* p, u64 x, u64 y) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(x), "l"(y) : "memory");
+}
+
+// One warp; lane i holds the i-th key of this rank's final (ascending) list.  Non-root: send it.
+// Root: fold every peer's list in as it arrives and acknowledge.  Returns the list to publish.
+// A rank that never delivers (it died, or the caller broke the collective contract) ends the wait after
+// ~4 s of SM clock with *status = 1; the host turns that into an error.
+__device__ __forceinline__ u64 mailbox_exchange32(u64 v, const Mailbox& mb, u32 k, int lane) {
+    constexpr long long kGiveUp = 1ll << 33;
+    if (mb.send) {
+        if (mb.seq > kMbDepth) {  // flow control: root must be done with the slot's previous use
+            const long long t0 = clock64();
+            bool ok = true;
+            if (lane == 0) {
+                while (*reinterpret_cast<const volatile u32*>(mb.ack_local) + kMbDepth < mb.seq) {
+                    if (clock64() - t0 > kGiveUp) {
+                        ok = false;
+                        break;
+                    }
+                }
+                if (!ok) *reinterpret_cast<volatile u32*>(mb.status) = 1;
+            }
+            __syncwarp();
+        }
+        st_volatile_v2(mb.send + lane, (u32)lane < k ? v : kKeyMax, (u64)mb.seq);
+        return v;
+    }
+    if (!mb.recv) return v;
+    const long long t0 = clock64();
+    for (u32 r = 1; r < mb.n_ranks; r++) {
+        ulonglong2 e;
+        bool have = false;
+        while (true) {
+            if (!have) {
+                e = ld_volatile_v2(mb.recv + (size_t)r * kMbSlots + lane);
+                have = e.y == (u64)mb.seq;
+            }
+            if (__all_sync(0xFFFFFFFFu, have)) break;
+            // lane 0 decides for the warp, so that every lane leaves in the same iteration
+            if (__shfl_sync(0xFFFFFFFFu, (int)(clock64() - t0 > kGiveUp), 0)) {
+                if (lane == 0) *reinterpret_cast<volatile u32*>(mb.status) = 1;
+                e.x = have ? e.x : kKeyMax;
+                break;
+            }
+        }
+        const u64 their_best = __shfl_sync(0xFFFFFFFFu, e.x, 0);
+        const u64 my_kth = __shfl_sync(0xFFFFFFFFu, v, (int)k - 1);
+        if (their_best < my_kth) v = warp_merge32(v, e.x, lane);
+    }
+    // acknowledge: the slot may be overwritten by search seq + kMbDepth
+    if (lane > 0 && (u32)lane < mb.n_ranks) *reinterpret_cast<volatile u32*>(mb.ack_remote[lane]) = mb.seq;
+    return v;
+}
+
 // Optional outputs of the fused final stage (see scan_epilogue); all indexed by query
 struct FinalOut {
     u32* done_counter;  // zero before the launch; the last CTA to finish resets it
@@ -404,8 +507,23 @@ struct FinalOut {
     u64* idx;           // [nq][k]  or nullptr
     float* dist;        // [nq][k]
     u32* count;         // [nq]
+    // When idx/dist/count live in pinned host memory (bsr_search, small results): after they are
+    // written the last CTA publishes `flag_value` here (same pinned block), system-fenced behind
+    // them, and the host picks the result up by polling instead of waiting for the whole grid to
+    // retire and the stream to signal.  nullptr: no flag.
+    u32* host_flag;
+    u32 flag_value;
+    Mailbox mb;         // cross-rank exchange fused into the last CTA (k <= 32, one query); all-null: none
     unsigned long long* dbg;  // debug stamps (see ScanArgs::dbg)
 };
+
+// end of the fused final stage: every result write of this CTA is ordered before the flag
+__device__ __forceinline__ void publish_host_flag(const FinalOut& fo) {
+    if (!fo.host_flag) return;  // kernel-uniform
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile u32*>(fo.host_flag) = fo.flag_value;
+}
 
 #ifdef BSR_TC_TIMELINE
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -467,9 +585,12 @@ __device__ __forceinline__ void fold_cta_lists(const u64* src, u32 n_lists, u64 
 // (lists[q][w][K] in shared memory) to the CTA's best K and publish them to
 // cta_keys[q][cta][K]; when the launch fuses the final stage (K == 32) the last CTA to finish
 // merges every CTA's list and unpacks the result, so a whole search is one kernel.
+// `live` = warps of this CTA that scanned at least one panel (the others' lists are still all KEY_MAX):
+// only those lists take part in the CTA-level reduce -- on a small store that is one or two of them.
 template <int W, int NQ>
 __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta_keys,
-                                              const FinalOut& fo, bool fuse_final, u32* panel_ticket = nullptr) {
+                                              const FinalOut& fo, bool fuse_final, u32* panel_ticket = nullptr,
+                                              u32 live = W) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ u32 s_is_last;
     const size_t q_stride = (size_t)gridDim.x * K;  // between queries in cta_keys
@@ -477,14 +598,15 @@ __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta
         // warp w reduces queries w, w+W, ... entirely in registers
         for (int q = warp; q < NQ; q += W) {
             u64 v = lists[((size_t)q * W) * 32 + lane];
-#pragma unroll
-            for (int w = 1; w < W; w++) v = warp_merge32(v, lists[((size_t)q * W + w) * 32 + lane], lane);
+            for (u32 w = 1; w < live; w++) v = warp_merge32(v, lists[((size_t)q * W + w) * 32 + lane], lane);
             cta_keys[q * q_stride + (size_t)blockIdx.x * 32 + lane] = v;
         }
     } else {
+        u32 live2 = 1;  // lists to reduce, rounded up to a power of two (the extra ones are empty)
+        while (live2 < live) live2 <<= 1;
         for (int q = 0; q < NQ; q++) {
             u64* ql = lists + (size_t)q * W * K;
-            cta_merge_lists(ql, W, K);
+            cta_merge_lists(ql, live2, K);
             for (u32 j = tid; j < K; j += W * 32) cta_keys[q * q_stride + (size_t)blockIdx.x * K + j] = ql[j];
         }
     }
@@ -548,6 +670,7 @@ __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta
             }
         }
         if (tid == 0) *fo.done_counter = 0;
+        publish_host_flag(fo);
         BSR_STAMP(fo.dbg, tid == 0, 10);
         return;
     }
@@ -567,9 +690,11 @@ __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta
             }
 #pragma unroll
             for (u32 i = 0; i < 20; i++) {
+                // only the first k keys of the result are ever read: a list whose best key is not below
+                // my k-th best cannot change them
                 const u64 their_best = __shfl_sync(0xFFFFFFFFu, t[i], 0);
-                const u64 my_worst = __shfl_sync(0xFFFFFFFFu, v, 31);
-                if (their_best < my_worst) v = warp_merge32(v, t[i], lane);
+                const u64 my_kth = __shfl_sync(0xFFFFFFFFu, v, (int)k - 1);
+                if (their_best < my_kth) v = warp_merge32(v, t[i], lane);
             }
         }
         lists[((size_t)q * W + warp) * 32 + lane] = v;
@@ -580,6 +705,7 @@ __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta
         u64 v = lists[((size_t)q * W) * 32 + lane];
 #pragma unroll
         for (int w = 1; w < W; w++) v = warp_merge32(v, lists[((size_t)q * W + w) * 32 + lane], lane);
+        if (NQ == 1) v = mailbox_exchange32(v, fo.mb, k, lane);  // multi-rank: send to root / fold the peers in
         fo.keys[(size_t)q * 32 + lane] = (u32)lane < k ? v : kKeyMax;  // slots past top_k are published empty
         if (fo.idx) {
             const bool ok = (u32)lane < k && v != kKeyMax;
@@ -592,6 +718,7 @@ __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta
         }
     }
     if (tid == 0) *fo.done_counter = 0;
+    publish_host_flag(fo);
     BSR_STAMP(fo.dbg, tid == 0, 10);
 }
 
@@ -781,7 +908,15 @@ struct BulkScanArgs {
     // of the scan time), with tickets it ends within one panel time (~16 us).  nullptr: static deal.
     // Zero before the launch; the last CTA to finish resets it (needs ScanArgs::fin.done_counter).
     u32* panel_ticket;
+    // Single host query (bsr_search, dim <= kParamQueryMax): the query travels in the kernel's
+    // parameter block (constant bank) instead of a separate host-to-device copy.
+    u32 query_in_params;
+    // ... and its magnitude |b| (src/metrics.rs:155, the same sequential fold, done once on the host)
+    // so that no warp runs the second 768-step chain next to its first panel's dot products.
+    float qparam_mag;
+    float qparam[768];
 };
+constexpr u32 kParamQueryMax = 768;
 
 // QB queries share one pass over the store: the row chunk is read from shared memory once and
 // feeds QB independent sequential dot products (a.query -> [QB][dim], outputs indexed by query).
@@ -790,7 +925,7 @@ struct BulkScanArgs {
 // W = warps per CTA: 8 (default), or 16 for small stores, where a second round of panels on a few
 // warps would otherwise double the (latency-bound) run time.
 template <int QB, bool BF16, int W = kBulkWarps>
-__global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkScanArgs ba) {
+__global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const __grid_constant__ BulkScanArgs ba) {
     const ScanArgs& a = ba.s;
     constexpr int CH = kChunkQuads;                    // fp32: column-quads per 4 KiB chunk
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -873,7 +1008,8 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
     // stage the queries, zero-padded to the padded column count
     for (u32 t = tid; t < (u32)QB * dq; t += (W * 32)) {
         const u32 b = t / dq, j = t - b * dq, c = 4 * j;
-        const float* qp = a.query + (size_t)b * a.dim;
+        // (parameter-block queries: one query, dim <= kParamQueryMax -- the host guarantees it)
+        const float* qp = ba.query_in_params ? ba.qparam : a.query + (size_t)b * a.dim;
         float4 v;
         v.x = (c + 0 < a.dim) ? qp[c + 0] : 0.0f;
         v.y = (c + 1 < a.dim) ? qp[c + 1] : 0.0f;
@@ -897,6 +1033,10 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
     bool need_qnorm = true;
 #pragma unroll
     for (int b = 0; b < QB; b++) mag_b[b] = qsq[b] = acc[b] = 0.0f;
+    if (QB == 1 && ba.query_in_params) {  // |b| came with the query
+        mag_b[0] = ba.qparam_mag;
+        need_qnorm = false;
+    }
 
     u32 stage = 0, parity = 0, ci = 0, panel = panel0;
     float mag_a = 0.0f;
@@ -998,7 +1138,7 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
                         if ((maybe_mask >> b) & 1u) {
                             bool d = false;
 #pragma unroll
-                            for (int u = 0; u < CH; u++) d |= differs4(v[u], sq[(j0 + u) * QB + b]);
+                            for (int u = 0; u < CH; u++) d |= differs4_fast(v[u], sq[(j0 + u) * QB + b]);
                             if (d) maybe_mask &= ~(1u << b);
                         }
                     }
@@ -1026,7 +1166,7 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
                         const float4 v = sp[u * 32];
 #pragma unroll
                         for (int b = 0; b < QB; b++)
-                            if (((maybe_mask >> b) & 1u) && differs4(v, sq[(j0 + u) * QB + b])) maybe_mask &= ~(1u << b);
+                            if (((maybe_mask >> b) & 1u) && differs4_fast(v, sq[(j0 + u) * QB + b])) maybe_mask &= ~(1u << b);
                     }
                 }
             } else {
@@ -1082,7 +1222,10 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const BulkSca
     for (int b = 0; b < QB; b++) top[b].finish(lane);
     __syncthreads();
     BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 5);
-    scan_epilogue<W, QB>(lists, K, a.k, a.cta_keys, a.fin, a.fuse_final != 0, ba.panel_ticket);
+    // warps that scanned a panel: with the CTA-first deal those are warps 0 .. live-1
+    const u32 cta_panels = blockIdx.x < a.n_panels ? (a.n_panels - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    scan_epilogue<W, QB>(lists, K, a.k, a.cta_keys, a.fin, a.fuse_final != 0, ba.panel_ticket,
+                         min(cta_panels, (u32)W));
 }
 
 #ifndef BSR_TEMPLATES_ONLY  // the plain (non-template) kernels are compiled once, in bsr_api.cu
@@ -1173,6 +1316,25 @@ __global__ void __launch_bounds__(32) merge32_kernel(const u64* __restrict__ in,
         const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
         if (lane == 0) count[q] = (u32)__popc(m);
     }
+}
+
+// The mailbox exchange for a rank that has nothing of its own to contribute (empty shard, or a local
+// scan that failed: the reference's empty list, metrics.rs:185-191): send an empty list / fold the
+// peers' lists, then publish like the scan's last CTA does.  One warp.
+__global__ void __launch_bounds__(32) mailbox_only_kernel(const FinalOut fo, u32 k) {
+    const int lane = threadIdx.x;
+    const u64 v = mailbox_exchange32(kKeyMax, fo.mb, k, lane);
+    if (fo.keys) fo.keys[lane] = (u32)lane < k ? v : kKeyMax;
+    if (fo.idx) {
+        const bool ok = (u32)lane < k && v != kKeyMax;
+        if ((u32)lane < k) {
+            fo.idx[lane] = ok ? (v & 0xFFFFFFFFull) : 0ull;
+            fo.dist[lane] = ok ? __uint_as_float(bits_from_ordered((u32)(v >> 32))) : 0.0f;
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+        if (lane == 0) fo.count[0] = (u32)__popc(m);
+    }
+    publish_host_flag(fo);
 }
 
 // candidates[q][K] -> idx[q][k] (u64, as the reference's usize), dist[q][k], count[q]

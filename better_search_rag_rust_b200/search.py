@@ -203,6 +203,31 @@ class BsrComm:
         _lib.check(_lib.lib().bsr_search_parallel(engine.store.handle, self._h, q.ctypes.data, nq, top_k, *args))
         return (idx, dist, count) if self.rank == 0 else None
 
+    def search_device(self, engine: "CudaShardEngine", queries, top_k: int, out=None):
+        """bsr_search_parallel_device: the same collective, device-resident and asynchronous on the
+        current torch stream.  `queries` is a CUDA tensor [nq, dim]; returns the int64 tensor
+        [nq, slots] of merged candidate keys (meaningful on rank 0)."""
+        import torch
+        dev = torch.device("cuda", engine.store.device)
+        q = queries.to(device=dev, dtype=torch.float32).contiguous()
+        if q.dim() == 1:
+            q = q.reshape(1, -1)
+        if q.shape[1] != engine.store.dim:
+            raise BsrError(_lib.BSR_ERR_INVALID, "query length differs from the store's dimension")
+        if out is None:
+            out = torch.empty((q.shape[0], candidate_slots(top_k)), dtype=torch.int64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.lib().bsr_search_parallel_device(engine.store.handle, self._h, q.data_ptr(), q.shape[0],
+                                                         top_k, out.data_ptr(), C.c_void_p(stream)))
+        return out
+
+    def uses_mailbox(self) -> bool:
+        """True when single-query top_k <= 32 searches exchange candidates through NVLink peer stores
+        fused into the scan kernel instead of ncclAllGather + a merge launch."""
+        yes = C.c_int()
+        _lib.check(_lib.lib().bsr_comm_uses_mailbox(self._h, C.byref(yes)))
+        return bool(yes.value)
+
     def close(self) -> None:
         if self._h:
             _lib.lib().bsr_comm_destroy(self._h)

@@ -196,10 +196,29 @@ BSR_API int bsr_comm_destroy(bsr_comm *comm);
 /* parallel_top_k_similarity_search (metrics.rs:174-206).  Collective: every rank passes its shard
  * and the same queries (host memory).  Scan of the local shard -> all-gather of the candidate slots
  * -> on root: on-device merge, unpack, copy to the host outputs (as bsr_search).  On the other
- * ranks the outputs are not written (the reference returns None there); they may be NULL. */
+ * ranks the outputs are not written (the reference returns None there); they may be NULL.
+ * A rank whose local scan fails still joins the exchange with an empty list (the reference's
+ * behaviour, metrics.rs:185-191) and returns its error afterwards; the other ranks complete.
+ * Single queries with top_k <= 32 skip the collective call altogether when the communicator has a
+ * mailbox (bsr_comm_uses_mailbox). */
 BSR_API int bsr_search_parallel(bsr_store *shard, bsr_comm *comm, const float *queries,
                                 uint32_t n_queries, uint32_t top_k, uint64_t *out_idx,
                                 float *out_dist, uint32_t *out_count);
+
+/* The same collective with device-resident queries and candidates, asynchronous on `stream` (what a
+ * host keeps in flight back to back).  On root d_candidates[n_queries][slots] receives the merged
+ * candidates of the whole store; on the other ranks its contents are unspecified. */
+BSR_API int bsr_search_parallel_device(bsr_store *shard, bsr_comm *comm, const float *d_queries,
+                                       uint32_t n_queries, uint32_t top_k, uint64_t *d_candidates,
+                                       void *stream);
+
+/* 1 when this communicator exchanges single-query, top_k <= 32 candidates through the NVLink mailbox
+ * (peer stores from the scan's last CTA into root's HBM, folded in by root's last CTA: one kernel per
+ * rank and search, no collective call); 0 when every search uses ncclAllGather + a merge launch
+ * (ranks in one process, two ranks on one GPU, no peer access, BSR_NO_MAILBOX set at create time).
+ * The per-handle option "no_mailbox" selects the ncclAllGather path for one shard's searches; it must
+ * be set identically on every rank. */
+BSR_API int bsr_comm_uses_mailbox(const bsr_comm *comm, int *yes);
 
 /* BF16 stores only: query batches of at least `min_batch` queries (default 32) are scanned on the
  * tensor cores (tcgen05, queries in tensor memory).  That path is not bit-exact: the tensor core

@@ -73,6 +73,10 @@ pub mod ffi {
         pub fn bsr_search_parallel(shard: *mut bsr_store, comm: *mut bsr_comm, queries: *const f32,
                                    n_queries: u32, top_k: u32, out_idx: *mut u64, out_dist: *mut f32,
                                    out_count: *mut u32) -> c_int;
+        pub fn bsr_search_parallel_device(shard: *mut bsr_store, comm: *mut bsr_comm, d_queries: *const f32,
+                                          n_queries: u32, top_k: u32, d_candidates: *mut u64,
+                                          stream: *mut c_void) -> c_int;
+        pub fn bsr_comm_uses_mailbox(comm: *const bsr_comm, yes: *mut c_int) -> c_int;
         pub fn bsr_store_set_tensor_min_batch(store: *mut bsr_store, min_batch: u32) -> c_int;
         pub fn bsr_store_set_option(store: *mut bsr_store, name: *const c_char, value: i64) -> c_int;
         pub fn bsr_store_launch_count(store: *const bsr_store, n_launches: *mut u64) -> c_int;
