@@ -78,6 +78,7 @@ struct Knobs {
     int tc_stats = 0;        // BSR_TC_STATS
     int wide = -1;           // BSR_WIDE: 16-warp CTAs: -1 auto (small f32 stores, every bf16 store), 0 never, 1 always
     int no_tickets = 0;      // BSR_NO_TICKETS: static panel deal on large stores too
+    int no_f32_tensor = 0;   // BSR_NO_F32_TENSOR: fp32 stores answer every batch with the exact scan (no bf16 shadow)
     int no_param_query = 0;  // BSR_NO_PARAM_QUERY: bsr_search always copies the query and waits on the stream
     int no_pdl = 0;          // BSR_NO_PDL: plain stream-ordered launches for back-to-back scans
     int no_mailbox = 0;      // BSR_NO_MAILBOX: cross-rank exchange through ncclAllGather only
@@ -103,6 +104,7 @@ static const Knobs& knobs() {
         v.tc_stats = getenv("BSR_TC_STATS") != nullptr;
         v.wide = geti("BSR_WIDE", -1);
         v.no_tickets = getenv("BSR_NO_TICKETS") != nullptr;
+        v.no_f32_tensor = getenv("BSR_NO_F32_TENSOR") != nullptr;
         v.no_param_query = getenv("BSR_NO_PARAM_QUERY") != nullptr;
         v.no_pdl = getenv("BSR_NO_PDL") != nullptr;
         v.no_mailbox = getenv("BSR_NO_MAILBOX") != nullptr;
@@ -137,7 +139,12 @@ struct bsr_store {
     size_t smem_optin = 0;
 
     // per-search scratch (grown on demand)
-    DevBuf cta_keys, merge_a, merge_b, d_queries, d_cand, d_result, d_counter, d_gtau, d_surv, d_gather, staging, ones;
+    DevBuf cta_keys, merge_a, merge_b, d_queries, d_cand, d_result, d_counter, d_gtau, d_surv, d_gather, staging, ones,
+        shadow, d_maxnorm, d_query1;
+    // fp32 stores: bf16 copy of the rows in the tensor path's tile layout, the FILTER operand of batched
+    // searches (built on the first such search, extended after appends); rows [0, shadow_rows) are valid
+    u64 shadow_rows = 0;
+    float max_norm = -1.0f;  // largest |a| of the shard (BSR_DOT filter margin); < 0: not computed yet
     u32 tensor_min_batch = 32;  // BF16 stores: batches at least this large use the tcgen05 path (0 = never)
     void* h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
@@ -344,7 +351,8 @@ extern "C" int bsr_store_destroy(bsr_store* s) {
     if (s->busy) cudaEventSynchronize(s->ev_busy);
     cudaStreamSynchronize(s->stream);
     DevBuf* bufs[] = {&s->cta_keys, &s->merge_a, &s->merge_b, &s->d_queries,
-                      &s->d_cand,   &s->d_result, &s->d_counter, &s->d_gtau, &s->d_surv, &s->d_gather, &s->staging, &s->ones};
+                      &s->d_cand,   &s->d_result, &s->d_counter, &s->d_gtau, &s->d_surv, &s->d_gather, &s->staging, &s->ones,
+                      &s->shadow,   &s->d_maxnorm, &s->d_query1};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (s->panels) cudaFree(s->panels);
@@ -372,6 +380,8 @@ extern "C" int bsr_store_reset(bsr_store* s) {
         CU(cudaStreamSynchronize(s->stream));
     }
     s->n_rows = 0;
+    s->shadow_rows = 0;
+    s->max_norm = -1.0f;
     return BSR_OK;
 }
 
@@ -394,6 +404,7 @@ static int finish_append(bsr_store* s, u64 n_rows) {
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s->stream));
     s->n_rows += n_rows;
+    s->max_norm = -1.0f;
     return BSR_OK;
 }
 
@@ -769,8 +780,51 @@ static u32 tensor_stages(const bsr_store* s, u32 mode) {
     return st;
 }
 static bool tensor_eligible(const bsr_store* s, u32 nq, u32 K) {
-    return is_bf16(s) && s->tensor_min_batch > 0 && nq >= s->tensor_min_batch && s->kb <= kTcMaxKB &&
-           K <= 128 && tensor_stages(s, 0) >= 2 && tensor_stages(s, 1) >= 2 && tensor_stages(s, 2) >= 2;
+    return (is_bf16(s) || !s->kn.no_f32_tensor) && s->tensor_min_batch > 0 && nq >= s->tensor_min_batch &&
+           s->kb <= kTcMaxKB && K <= BSR_MAX_TOP_K && tensor_stages(s, 0) >= 2 && tensor_stages(s, 1) >= 2 &&
+           tensor_stages(s, 2) >= 2;
+}
+
+// fp32 store: bring the bf16 shadow (and 1/|a|) up to date with the rows
+static int ensure_shadow(bsr_store* s, cudaStream_t st) {
+    if (is_bf16(s) || s->shadow_rows == s->n_rows) return BSR_OK;
+    const size_t tiles_cap = (size_t)((s->cap_rows + 63) / 64);
+    const size_t need = tiles_cap * s->kb * kTileBytes;
+    if (s->shadow.bytes < need) {  // (re)allocated: everything is converted again
+        TRY(ensure(s->shadow, need));
+        s->shadow_rows = 0;
+    }
+    const u32 lo = (u32)s->shadow_rows, hi = (u32)s->n_rows;
+    const u32 first_tile = lo >> 6, last_tile = (hi - 1) >> 6;
+    const size_t total = (size_t)(last_tile - first_tile + 1) * s->kb * 512;
+    const size_t per_tile = (size_t)s->kb * 512;
+    const size_t step = (((size_t)1 << 30) / per_tile) * per_tile;  // whole tiles, grid within 32-bit thread counts
+    for (size_t done = 0; done < total; done += step) {
+        const size_t n = std::min(total - done, step);
+        const u32 tile0 = first_tile + (u32)(done / per_tile);
+        shadow_from_panels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+            s->panels, (uint4*)s->shadow.p, s->norms, s->inv_norms, done ? tile0 * 64 : lo, hi, s->dim, s->dq, s->kb);
+        s->launches++;
+        CU(cudaGetLastError());
+    }
+    s->shadow_rows = s->n_rows;
+    return BSR_OK;
+}
+
+// largest |a| of the shard (finite norms only), for the BSR_DOT filter margin
+static int ensure_max_norm(bsr_store* s, cudaStream_t st) {
+    if (s->max_norm >= 0.0f) return BSR_OK;
+    TRY(ensure(s->d_maxnorm, 256));
+    CU(cudaMemsetAsync(s->d_maxnorm.p, 0, 4, st));
+    max_norm_kernel<<<std::min<unsigned>(1024, (unsigned)((s->n_rows + 255) / 256)), 256, 0, st>>>(
+        s->norms, (u32)s->n_rows, (u32*)s->d_maxnorm.p);
+    s->launches++;
+    CU(cudaGetLastError());
+    float m = 0.0f;
+    CU(cudaMemcpyAsync(&m, s->d_maxnorm.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    s->max_norm = m;
+    return BSR_OK;
 }
 
 template <int MODE>
@@ -804,6 +858,17 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
                          float* d_dist, u32* d_count, cudaStream_t st) {
     const u32 K = bsr_candidate_slots(k);
     const u32 n_tiles = (u32)((s->n_rows + kTcN - 1) / kTcN);
+    TRY(ensure_shadow(s, st));
+    // Filter margin (TensorScanArgs::margin): twice the worst-case gap between the filter's dot product
+    // and the exact one, relative to |a| |b|.  Query rounded to bf16: 2^-9 per element; an fp32 store's
+    // shadow rows another 2^-9; 1e-4 covers both accumulations (768 * 2^-24 for the sequential fold,
+    // less for the tensor core) and the second-order terms.
+    float margin = 2.0f * ((is_bf16(s) ? 1.0f : 2.0f) * 0.001953125f + 1e-4f);
+    if (s->metric == BSR_DOT) {  // scores are not divided by |a|: scale by the largest one
+        TRY(ensure_max_norm(s, st));
+        margin *= s->max_norm;
+    }
+    const u32 surv_cap = std::max<u32>(kTcSurvivorCap, 2 * K);
     // more than one 128-query group: clusters of 2 CTAs share every store tile (TMA multicast)
     // mode 0: single CTAs; 1: clusters of 2 with multicast tiles; 2: CTA pairs (cta_group::2)
     u32 mode = (nq > kTcQ && s->n_sm >= 2) ? 2u : 0u;  // measured: pairs (2) beat multicast (1) by ~6 %
@@ -819,8 +884,8 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
     TRY(ensure(s->cta_keys, (size_t)nq * n_clusters * K * sizeof(u64)));
     const size_t gm_bytes = (size_t)QS * ((k + kTcN - 1) / kTcN) * kTcN * sizeof(u32);
     TRY(ensure(s->d_gtau, gm_bytes));
-    const size_t surv_bytes = (size_t)QS * n_clusters * 2 * kTcSurvivorCap * sizeof(u64);
-    TRY(ensure(s->d_surv, surv_bytes + (size_t)QS * n_clusters * sizeof(u32) + QS * sizeof(float)));
+    const size_t surv_bytes = (size_t)QS * n_clusters * 2 * surv_cap * sizeof(u64);
+    TRY(ensure(s->d_surv, surv_bytes + (size_t)QS * n_clusters * sizeof(u32) + 2 * QS * sizeof(float)));
     const u32 max_per_cta = std::max<u32>(2, kMergeMaxKeys / K);
     const size_t inter = (size_t)nq * ((n_clusters + max_per_cta - 1) / max_per_cta) * K * sizeof(u64);
     TRY(ensure(s->merge_a, inter));
@@ -835,7 +900,11 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
     CU(cudaEventRecord(s->ev_scan0, st));
     for (u32 q0 = 0; q0 < nq; q0 += QS) {
         TensorScanArgs a;
-        a.tiles = (const unsigned char*)s->panels;
+        a.tiles = is_bf16(s) ? (const unsigned char*)s->panels : (const unsigned char*)s->shadow.p;
+        a.exact_panels = is_bf16(s) ? nullptr : s->panels;
+        a.exact_dq = s->dq;
+        a.margin = margin;
+        a.surv_cap = surv_cap;
         a.norms = s->norms;
         a.inv_norms = s->inv_norms;
         a.queries = d_queries + (size_t)q0 * s->dim;
@@ -844,6 +913,7 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
         a.survivors = (u64*)s->d_surv.p;
         a.surv_count = (u32*)((char*)s->d_surv.p + surv_bytes);
         a.q_mag = (float*)(a.surv_count + (size_t)QS * n_clusters);
+        a.q_thr = a.q_mag + QS;
         a.nq_valid = std::min(QS, nq - q0);
         a.n_rows = (u32)s->n_rows;
         a.n_tiles = n_tiles;
@@ -879,8 +949,17 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
         else if (mode == 1) TRY(launch_tensor<1>(s, a, grid, smem, st));
         else TRY(launch_tensor<0>(s, a, grid, smem, st));
         {
-            const u32 lists = a.nq_valid * n_clusters, wpb = 4;  // 4 warps x 8 KiB of sort scratch per CTA
-            finalize_survivors_kernel<<<(lists + wpb - 1) / wpb, wpb * 32, wpb * kTcSurvivorCap * sizeof(u64), st>>>(
+            const u32 lists = a.nq_valid * n_clusters, wpb = 4;  // 4 warps x surv_cap keys of sort scratch per CTA
+            static thread_local bool fin_configured[64] = {false};
+            if (!fin_configured[s->device & 63]) {
+                CU(cudaFuncSetAttribute(finalize_survivors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(4 * 2 * BSR_MAX_TOP_K * sizeof(u64))));
+                fin_configured[s->device & 63] = true;
+            }
+            survivor_threshold_kernel<<<a.nq_valid, 256, 0, st>>>(a, n_clusters);
+            s->launches++;
+            CU(cudaGetLastError());
+            finalize_survivors_kernel<<<(lists + wpb - 1) / wpb, wpb * 32, (size_t)wpb * surv_cap * sizeof(u64), st>>>(
                 a, n_clusters);
             s->launches++;
             CU(cudaGetLastError());
@@ -936,7 +1015,17 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
 static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 k, u64* d_cand,
                               u64* d_idx, float* d_dist, u32* d_count, cudaStream_t st) {
     const u32 K = bsr_candidate_slots(k);
-    if (tensor_eligible(s, nq, K)) return search_tensor(s, d_queries, nq, k, d_cand, d_idx, d_dist, d_count, st);
+    if (tensor_eligible(s, nq, K)) {
+        // in slices that keep the per-cluster candidate lists (slice x clusters x K keys) within 1 GiB
+        const u32 per = std::max<u32>(256, (u32)((((size_t)1 << 30) / ((size_t)s->n_sm * K * sizeof(u64))) / 256 * 256));
+        for (u32 q0 = 0; q0 < nq; q0 += per) {
+            const u32 n = std::min(per, nq - q0);
+            TRY(search_tensor(s, d_queries + (size_t)q0 * s->dim, n, k, d_cand + (size_t)q0 * K,
+                              d_idx ? d_idx + (size_t)q0 * k : nullptr, d_idx ? d_dist + (size_t)q0 * k : nullptr,
+                              d_idx ? d_count + q0 : nullptr, st));
+        }
+        return BSR_OK;
+    }
     const u32 n_panels = (u32)((s->n_rows + 31) / 32);
     const bool bulk = (scan_variant(s) == 1 || is_bf16(s)) && bulk_stages(s, K, 1) >= 2;
     CHECK(bulk || !is_bf16(s), BSR_ERR_UNSUPPORTED, "search: BF16 stores need the bulk-async scan kernel");
@@ -1207,12 +1296,49 @@ extern "C" int bsr_search(bsr_store* s, const float* queries, uint32_t nq, uint3
         *flag = 0;  // whatever an earlier call left in this word of the shared pinned block
     } else {
         memcpy(h, queries, qbytes);
-        CU(cudaMemcpyAsync(s->d_queries.p, h, qbytes, cudaMemcpyHostToDevice, s->stream));
     }
+    // Batches on the tensor path: a query without a usable direction (zero, denormal-small, NaN or inf
+    // magnitude) cannot be bounded by the filter -- every row would survive it and stall its whole
+    // launch -- so such queries ride along as a copy of a well-formed one and are answered afterwards,
+    // one by one, by the exact scan (same results: both paths end in the reference's arithmetic).
+    std::vector<u32> degenerate;
+    const u32 saved_min_batch = s->tensor_min_batch;
+    if (!one_launch && tensor_eligible(s, nq, K)) {
+        u32 good = nq;
+        for (u32 q = 0; q < nq; q++) {
+            double ss = 0.0;
+            for (u32 c = 0; c < s->dim; c++) ss += (double)queries[(size_t)q * s->dim + c] * (double)queries[(size_t)q * s->dim + c];
+            if (!(ss >= 1e-10) || !(ss < 1e37)) degenerate.push_back(q);  // zero / tiny / NaN / inf / |b|^2 near FLT_MAX
+            else if (good == nq) good = q;
+        }
+        if (good == nq) {
+            s->tensor_min_batch = 0;  // nothing but degenerate queries: the exact scan answers the batch
+            degenerate.clear();
+        } else {
+            for (u32 q : degenerate)
+                memcpy(h + (size_t)q * s->dim * sizeof(float), queries + (size_t)good * s->dim, (size_t)s->dim * sizeof(float));
+        }
+    }
+    if (!one_launch) CU(cudaMemcpyAsync(s->d_queries.p, h, qbytes, cudaMemcpyHostToDevice, s->stream));
     int rc = search_device_impl(s, (const float*)s->d_queries.p, nq, k, (u64*)s->d_cand.p, (u64*)r,
                                 (float*)(r + ibytes), (u32*)(r + ibytes + dbytes), s->stream);
     s->param_query = nullptr;
     s->host_flag = nullptr;
+    for (size_t i = 0; i < degenerate.size() && rc == BSR_OK; i++) {
+        const u32 q = degenerate[i];
+        rc = ensure(s->d_query1, (size_t)s->dim * sizeof(float));
+        if (rc != BSR_OK) break;
+        if (cudaMemcpyAsync(s->d_query1.p, queries + (size_t)q * s->dim, (size_t)s->dim * sizeof(float),
+                            cudaMemcpyHostToDevice, s->stream) != cudaSuccess) {
+            rc = fail(BSR_ERR_CUDA, "bsr_search: query upload failed");
+            break;
+        }
+        s->tensor_min_batch = 0;
+        rc = search_device_impl(s, (const float*)s->d_query1.p, 1, k, (u64*)s->d_cand.p + (size_t)q * K,
+                                (u64*)r + (size_t)q * k, (float*)(r + ibytes) + (size_t)q * k,
+                                (u32*)(r + ibytes + dbytes) + q, s->stream);
+    }
+    s->tensor_min_batch = saved_min_batch;
     TRY(rc);
     if (one_launch) {
         TRY(wait_host_flag(s, flag, s->flag_seq));
@@ -1842,7 +1968,7 @@ extern "C" int bsr_store_set_option(bsr_store* s, const char* name, int64_t valu
         {"tensor_stages", &s->kn.tensor_stages}, {"tensor_stage_kb", &s->kn.tensor_stage_kb},
         {"tc_stats", &s->kn.tc_stats},         {"no_pdl", &s->kn.no_pdl},
         {"wide", &s->kn.wide},                 {"no_tickets", &s->kn.no_tickets},
-        {"no_param_query", &s->kn.no_param_query},
+        {"no_param_query", &s->kn.no_param_query}, {"no_f32_tensor", &s->kn.no_f32_tensor},
         {"no_mailbox", &s->kn.no_mailbox},
     };
     for (auto& t : table)

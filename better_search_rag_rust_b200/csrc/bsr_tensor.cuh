@@ -67,7 +67,7 @@ constexpr u32 kTcStageKB = 12;   // max 64-column blocks per ring stage: one cp.
                                  // thread issuing 8 KiB copies cannot keep an SM fed: ~300 cycles each)
 constexpr u32 kTcStageBytes = kTcStageKB * kTileBytes;
 constexpr u32 kTcLearnTiles = 8; // tiles scanned bound-only first, then again at the end
-constexpr u32 kTcSurvivorCap = 1024;  // survivor slots per (CTA, query)
+constexpr u32 kTcSurvivorCap = 1024;  // survivor slots per (CTA, query) for top_k <= 512; 2 x k_pad above (TensorScanArgs::surv_cap)
 constexpr u32 kTcNormSlots = 16; // ring of per-tile (|a|, 1/|a|) blocks brought in by TMA (the producer runs ~5 tiles ahead of the epilogue)
 
 struct TensorScanArgs {
@@ -79,10 +79,20 @@ struct TensorScanArgs {
     u32* g_gm;                   // [64*T][128*C] global class maxima (ordered-float bits), 0 before the launch
     u64* survivors;              // [128*C][n_clusters][2 * kTcSurvivorCap] raw (row, score) pairs
     u32* surv_count;             // [128*C][n_clusters] survivors per (query, cluster)
-    float* q_mag;                // [128*C] |b| of the bf16-rounded queries (written by cluster 0)
+    float* q_mag;                // [128*C] |b| of the queries as given (written by cluster 0)
+    float* q_thr;                // [128*C] final filter threshold per query (survivor_threshold_kernel)
     u32 nq_valid;                // <= 128 * cluster size
     u32 n_rows, n_tiles, KB, dim, k, k_pad, row_base, stages;
     u32 stage_kb;                // 64-column blocks per ring stage (<= kTcStageKB)
+    // The tensor cores are a FILTER: they see bf16-rounded queries (and, for an fp32 store, its bf16
+    // shadow), and every survivor's distance is then recomputed with the reference's own arithmetic
+    // (sequential binary32 fold over the stored row and the UNROUNDED query) -- results are bit-identical
+    // to the exact scan's.  `margin` widens the bound by twice the worst-case gap between the two dot
+    // products, in units of |a| * |b| (Cauchy-Schwarz on the element-wise rounding errors).
+    float margin;
+    const float4* exact_panels;  // fp32 store: the exact rows (panel layout); nullptr: `tiles` ARE the exact rows (bf16 store)
+    u32 exact_dq;                // fp32 store: column quads per row
+    u32 surv_cap;                // survivor slots per (cluster, query) list; the buffer holds 2 x surv_cap (compaction scratch)
     u32 metric;                  // bsr_metric: 0 cosine (scores scaled by 1/|a|), 1 dot (inv_norms -> 64 ones, stride 0)
     u32 norm_stride;             // rows between consecutive tiles' entries of norms / inv_norms (64, or 0 for BSR_DOT)
     long long* timeline;         // debug builds (-DBSR_TC_TIMELINE): [2 CTAs][kTlTiles][8] clock64 stamps
@@ -257,44 +267,60 @@ __device__ __forceinline__ void red_max_if(u32* addr, u32 val, bool pred) {
 __device__ __forceinline__ u32 f32_ordered(float f) { return ordered_from_bits(__float_as_uint(f)); }
 __device__ __forceinline__ float f32_from_ordered(u32 o) { return __uint_as_float(bits_from_ordered(o)); }
 
-// exact identity test of a store row against the bf16-rounded query (rare: only when sim ~ 1)
-__device__ __noinline__ bool row_equals_query_bf16(const unsigned char* tiles, u32 row, u32 KB, u32 dim,
-                                                   const float* q) {
-    for (u32 g = 0; g < KB * 8; g++) {
-        const uint4 a = *reinterpret_cast<const uint4*>(tiles + bf16_chunk_offset(row, g >> 3, g & 7u, KB));
-        const u32 w[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-            const u32 c = g * 8 + e;
-            const float qa = c < dim ? __uint_as_float((u32)f32_to_bf16_rne(q[c]) << 16) : 0.0f;
-            const float ra = (e & 1) ? bf16_hi(w[e >> 1]) : bf16_lo(w[e >> 1]);
-            if (differs(ra, qa)) return false;
-        }
-    }
-    return true;
-}
-
-// A survivor is stored raw: (local row << 32) | score bits.  Its exact distance -- the reference
-// formula, src/metrics.rs:148-164 -- is computed once, at the end of the kernel.
+// A survivor is stored raw: (local row << 32) | score bits.  The score only got it through the filter;
+// its distance is the reference's own arithmetic (src/metrics.rs:143-165) over the STORED row and the
+// query as given: sequential binary32 fold, identity test, zero-norm rule, clamp -- the same device
+// functions as the exact scan, so the key is bit-identical to the one the exact scan would produce.
 __device__ __forceinline__ u64 pack_survivor(u32 row, float score) {
     return ((u64)row << 32) | (u64)__float_as_uint(score);
 }
-__device__ __forceinline__ u64 survivor_key(const TensorScanArgs& a, u64 raw, float na, const float* qp, float mag_b) {
+__device__ __forceinline__ float4 load_query_quad(const float* qp, u32 c, u32 dim, bool vec_ok) {
+    if (vec_ok && c + 4 <= dim) return __ldg(reinterpret_cast<const float4*>(qp + c));
+    float4 q;
+    q.x = c + 0 < dim ? __ldg(qp + c + 0) : 0.0f;
+    q.y = c + 1 < dim ? __ldg(qp + c + 1) : 0.0f;
+    q.z = c + 2 < dim ? __ldg(qp + c + 2) : 0.0f;
+    q.w = c + 3 < dim ? __ldg(qp + c + 3) : 0.0f;
+    return q;
+}
+__device__ __noinline__ u64 survivor_key(const TensorScanArgs& a, u64 raw, float na, const float* qp, float mag_b) {
     const u32 row = (u32)(raw >> 32);
-    const float score = __uint_as_float((u32)raw);
-    if (a.metric) return make_key(__fsub_rn(1.0f, score), a.row_base + row);  // BSR_DOT
-    float dist = 1.0f;  // zero magnitude (src/metrics.rs:157-159)
-    // identity (src/metrics.rs:148-151) precedes every other rule; within 1e-10 per element implies
-    // sim ~ 1 unless the query is tiny (|b| < 1e-6), in which case every survivor is checked
-    bool maybe_identical = !(mag_b >= 1e-6f);
-    if (na != 0.0f && mag_b != 0.0f) {
-        float sim = __fdiv_rn(score, __fmul_rn(na, mag_b));
-        sim = fminf(fmaxf(sim, -1.0f), 1.0f);
-        dist = __fsub_rn(1.0f, sim);
-        maybe_identical |= sim >= 0.99999f;
+    const bool vec_ok = (a.dim % 4 == 0) && ((reinterpret_cast<size_t>(qp) & 15) == 0);
+    float acc = 0.0f;
+    bool identical = true;
+    // The row is read eight 16-byte pieces at a time, all eight loads in flight before the first is
+    // folded: a survivor's row is cold (DRAM latency), and the fold itself must stay sequential.
+    if (a.exact_panels) {  // fp32 store: panel layout, column quad j of row r at panels[((r/32)*dq + j)*32 + r%32]
+        const float4* p = a.exact_panels + (size_t)(row >> 5) * a.exact_dq * 32 + (row & 31u);
+        for (u32 j0 = 0; j0 < a.exact_dq; j0 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (u32 u = 0; u < 8; u++)
+                v[u] = j0 + u < a.exact_dq ? p[(size_t)(j0 + u) * 32] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+            for (u32 u = 0; u < 8; u++) {
+                if (j0 + u < a.exact_dq) {
+                    const float4 q = load_query_quad(qp, 4 * (j0 + u), a.dim, vec_ok);
+                    acc = dot4_seq(acc, v[u], q);
+                    identical = identical && !differs4(v[u], q);
+                }
+            }
+        }
+    } else {               // bf16 store: the tiles are the rows; 8 chunks = one 64-column block
+        for (u32 kb = 0; kb < a.KB; kb++) {
+            uint4 v[8];
+#pragma unroll
+            for (u32 u = 0; u < 8; u++) v[u] = *reinterpret_cast<const uint4*>(a.tiles + bf16_chunk_offset(row, kb, u, a.KB));
+#pragma unroll
+            for (u32 u = 0; u < 8; u++) {
+                const u32 c = kb * 64 + u * 8;
+                const float4 q0 = load_query_quad(qp, c, a.dim, vec_ok), q1 = load_query_quad(qp, c + 4, a.dim, vec_ok);
+                acc = dot8_seq_bf16(acc, v[u], q0, q1);
+                identical = identical && !differs8_bf16(v[u], q0, q1);
+            }
+        }
     }
-    if (maybe_identical && row_equals_query_bf16(a.tiles, row, a.KB, a.dim, qp)) dist = 0.0f;
-    return make_key(dist, a.row_base + row);
+    return make_key(finish_distance(acc, na, mag_b, identical, a.metric), a.row_base + row);
 }
 // Overflowing survivor buffer (adversarial row order only): keep, exactly, the k best of the cap
 // entries.  Out of line: it must not bloat the score loop.  Returns the exact k-th best key.
@@ -527,7 +553,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
         const bool active = q < a.nq_valid;
         const float* qp = a.queries + (size_t)(active ? q : 0) * a.dim;
         const u32 lane_addr = ((u32)(warp * 32) << 16);
-        float qsq = 0.0f;
+        float qsq = 0.0f, qsq_exact = 0.0f;  // |b|^2 of the rounded query (bound scale) and of the query itself (distances)
         const bool vec_ok = (a.dim % 4 == 0) && ((reinterpret_cast<size_t>(qp) & 15) == 0);
         // Every lane reads its own query row (3 KiB at a 3 KiB stride), so this loop is bound by L2
         // round trips: four 32-element blocks are fetched (32 independent 128-bit loads) before the
@@ -567,6 +593,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
                         const float flo = bf16_lo(r[e]), fhi = bf16_hi(r[e]);
                         qsq = __fadd_rn(qsq, __fmul_rn(flo, flo));  // |b| over the rounded query, sequential
                         qsq = __fadd_rn(qsq, __fmul_rn(fhi, fhi));
+                        // src/metrics.rs:155 on the query as given: columns in order, separately rounded
+                        qsq_exact = __fadd_rn(qsq_exact, __fmul_rn(f[u][2 * e], f[u][2 * e]));
+                        qsq_exact = __fadd_rn(qsq_exact, __fmul_rn(f[u][2 * e + 1], f[u][2 * e + 1]));
                     }
                     tmem_st16(tmem_a + lane_addr + cb * 16, r);
                 }
@@ -577,10 +606,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
         if (PAIR && crank != 0) mbar_arrive_cluster(smem_u32(aready_bar), 0);  // the leader issues the MMAs
         else mbar_arrive(smem_u32(aready_bar));
         const float mag_b = __fsqrt_rn(qsq);
+        const float mag_b_exact = __fsqrt_rn(qsq_exact);
         // The identity shortcut (src/metrics.rs:148-151) precedes every other rule.  Two vectors
         // within 1e-10 per element have sim ~ 1 unless the query itself is tiny (|b| < 1e-6): such
         // a query is never pruned and checks every row exactly.
-        const bool tiny_q = !a.metric && !(mag_b >= 1e-6f);
+        // (a NaN / inf element makes every score NaN: such a query prunes nothing either)
+        const bool tiny_q = !(mag_b >= 1e-6f) || !(mag_b_exact >= 1e-6f) || !(mag_b_exact < INFINITY);
 
         // classes: (row position in its tile) x (CTA group); this CTA owns 64 of the kc classes
         const u32 T = (a.k + kTcN - 1) / kTcN, kc = T * kTcN;
@@ -591,7 +622,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
         for (u32 j = 0; j < kTcN; j++) gmr[j] = -INFINITY;
 
         // survivor slots of this (CTA, query): the upper half doubles as scratch for a compaction
-        u64* surv_buf = a.survivors + ((size_t)q * n_clusters + cluster_id) * (2 * kTcSurvivorCap);
+        const u32 cap = a.surv_cap;
+        u64* surv_buf = a.survivors + ((size_t)q * n_clusters + cluster_id) * (2 * (size_t)cap);
         u32 surv_cnt = 0;
         float thr = -INFINITY;    // prune rows with t < thr, t = S / |a|
         u32 next_refresh = max(learn >> 1, 1u);  // refresh the bound after this many tiles of the sequence
@@ -659,7 +691,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
             }
             const float tmax = fmax3_nan(fmax3_nan(gmax[0], gmax[1], gmax[2]), gmax[3], gmax[3]);
             // NaN scores always survive (their exact distance decides)
-            if (__any_sync(0xFFFFFFFFu, !(tmax < pass_thr))) {
+            if (!learn_only && __any_sync(0xFFFFFFFFu, !(tmax < pass_thr))) {
                 // pass 2 -- only the 16-row groups where some lane of the warp can have a survivor:
                 // re-test each score and append the survivors (compile-time register index, predicated
                 // stores: no per-survivor loop, no register select)
@@ -667,9 +699,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
 #pragma unroll
                 for (u32 g = 0; g < 4; g++) {
                     if (__any_sync(0xFFFFFFFFu, !(gmax[g] < pass_thr))) {
-                        if (surv_cnt + 16 > kTcSurvivorCap) {
+                        if (surv_cnt + 16 > cap) {
                             // overflow (adversarial row order only): keep the exact best k
-                            compact_survivors(a, surv_buf, surv_cnt, qp, mag_b, surv_buf + kTcSurvivorCap);
+                            compact_survivors(a, surv_buf, surv_cnt, qp, mag_b_exact, surv_buf + cap);
                             surv_cnt = a.k;
                         }
 #pragma unroll
@@ -680,7 +712,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
                             for (u32 e = 0; e < 4; e++) {
                                 const u32 j = j4 * 4 + e;
                                 const float t = v[j] * ivs[e];
-                                if (!(t < pass_thr) && j < n_mine) surv_buf[surv_cnt++] = pack_survivor(row0 + j, v[j]);
+                                if (!(t < pass_thr) && j < n_mine) surv_buf[surv_cnt++] = pack_survivor(row0 + j, t);
                             }
                         }
                     }
@@ -718,10 +750,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
                                 bound = fminf(bound, their_bits[i] ? f32_from_ordered(their_bits[i]) : -INFINITY);
                         }
                     }
-                    // kc >= k distinct rows reach `bound`; keep a 1e-6 (in similarity) safety margin
-                    // (BSR_DOT ranks by the raw score itself: t == S, so the margin only has to be >= 0)
+                    // kc >= k distinct rows reach `bound` in the FILTER's arithmetic; a row can only be dropped
+                    // when even twice the worst-case filter error cannot lift it over them (a.margin, in units
+                    // of |b| for cosine -- t = S / |a| -- and of |a|max |b| <= ... for BSR_DOT see the host side)
                     thr = (bound == -INFINITY) ? -INFINITY
-                                               : bound - (a.metric ? 0.0f : 1e-6f * mag_b) - 1e-6f * fabsf(bound);
+                                               : bound - a.margin * mag_b_exact - 1e-6f * fabsf(bound);
                 }
             }
             if (tid == 0) BSR_TL(sq, 7);
@@ -729,7 +762,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
         // exact keys + sort of the survivors happen in finalize_survivors_kernel (fully parallel)
         if (active) {
             a.surv_count[(size_t)q * n_clusters + cluster_id] = surv_cnt;
-            if (cluster_id == 0) a.q_mag[q] = mag_b;
+            if (cluster_id == 0) a.q_mag[q] = mag_b_exact;
         }
     }
 
@@ -745,47 +778,167 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
 }
 
 #ifndef BSR_TEMPLATES_ONLY
-// One warp per (query, CTA) survivor list: raw (row, score) pairs -> exact keys (the reference's
-// distance formula) -> bitonic sort -> the best k_pad written as an ascending candidate list.
-__global__ void __launch_bounds__(256) finalize_survivors_kernel(const TensorScanArgs a, u32 n_cta) {
+// Per query, after the scan: the k-th largest filter score t among ALL its survivors (every cluster's
+// list) certifies k distinct rows at least that good -- a far tighter bound than the running one the scan
+// pruned with (which sits near rank kc * H(kc)).  Only survivors within the margin of it can be in the
+// exact top-k; the rest (~98 % of them) are dropped without ever touching their rows again.
+// One CTA per query; radix selection over the order-preserving bit image of t, 32 counting passes over
+// the values held in shared memory (or re-read from the lists when they do not fit).
+constexpr u32 kThrSmemValues = 12000;  // just under the 48 KiB of static shared memory
+__global__ void __launch_bounds__(256) survivor_threshold_kernel(const TensorScanArgs a, u32 n_cta) {
+    __shared__ u32 s_vals[kThrSmemValues];
+    __shared__ u32 s_count[8];
+    __shared__ u32 s_total;
+    const u32 q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 cap = a.surv_cap;
+    const u64* base = a.survivors + (size_t)q * n_cta * (2 * (size_t)cap);
+    const u32* counts = a.surv_count + (size_t)q * n_cta;
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    // gather the ordered images (a NaN score certifies nothing: image 0, below every number)
+    for (u32 l = 0; l < n_cta; l++) {
+        const u32 n = min(counts[l], cap);
+        if (tid == 0) s_total += n;  // running offset, advanced by one thread per list
+        __syncthreads();
+        const u32 off = s_total - n;
+        for (u32 j = tid; j < n; j += 256) {
+            const float t = __uint_as_float((u32)base[(size_t)l * (2 * (size_t)cap) + j]);
+            if (off + j < kThrSmemValues) s_vals[off + j] = (t == t) ? f32_ordered(t) : 0u;
+        }
+        __syncthreads();
+    }
+    const u32 total = s_total;
+    const bool in_smem = total <= kThrSmemValues;
+    auto count_ge = [&](u32 x) -> u32 {
+        u32 c = 0;
+        if (in_smem) {
+            for (u32 j = tid; j < total; j += 256) c += s_vals[j] >= x ? 1u : 0u;
+        } else {
+            for (u32 l = 0; l < n_cta; l++) {
+                const u32 n = min(counts[l], cap);
+                for (u32 j = tid; j < n; j += 256) {
+                    const float t = __uint_as_float((u32)base[(size_t)l * (2 * (size_t)cap) + j]);
+                    c += ((t == t) ? f32_ordered(t) : 0u) >= x ? 1u : 0u;
+                }
+            }
+        }
+        c = __reduce_add_sync(0xFFFFFFFFu, c);
+        __syncthreads();  // s_count of the previous pass has been read by everyone
+        if (lane == 0) s_count[warp] = c;
+        __syncthreads();
+        u32 sum = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) sum += s_count[w];
+        return sum;
+    };
+    float thr = -INFINITY;
+    if (count_ge(1u) >= a.k) {  // at least k survivors with a number for a score
+        u32 ans = 0;
+        for (int bit = 31; bit >= 0; bit--) {
+            const u32 cand = ans | (1u << bit);
+            if (count_ge(cand) >= a.k) ans = cand;
+        }
+        const float kth = f32_from_ordered(ans);  // k-th largest score
+        const float mag_b = a.q_mag[q];
+        thr = kth - a.margin * mag_b - 1e-6f * fabsf(kth);
+        if (!(mag_b >= 1e-6f) || !(mag_b < INFINITY)) thr = -INFINITY;  // no usable direction: every survivor is rescored
+    }
+    if (tid == 0) a.q_thr[q] = thr;
+}
+
+// One warp per (query, cluster) survivor list: the survivors that pass the query's final threshold get
+// their exact key (the reference's distance over the stored row, one survivor per lane), the keys are
+// sorted and the best k_pad written as an ascending candidate list.  Dynamic shared memory: surv_cap
+// keys of scratch per warp.
+__global__ void __launch_bounds__(128) finalize_survivors_kernel(const TensorScanArgs a, u32 n_cta) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u64* scratch = reinterpret_cast<u64*>(smem_raw) + (size_t)warp * kTcSurvivorCap;
+    const u32 cap = a.surv_cap;
+    u64* scratch = reinterpret_cast<u64*>(smem_raw) + (size_t)warp * cap;
     const u32 list = blockIdx.x * (blockDim.x >> 5) + warp;  // = q * n_cta + cta
     if (list >= a.nq_valid * n_cta) return;
     const u32 q = list / n_cta;
     const u32 K = a.k_pad;
-    const u32 n = min(a.surv_count[list], kTcSurvivorCap);
-    u32 P = K;
-    while (P < n) P <<= 1;
-    const u64* src = a.survivors + (size_t)list * (2 * kTcSurvivorCap);
+    const u32 n = min(a.surv_count[list], cap);
+    const u64* src = a.survivors + (size_t)list * (2 * (size_t)cap);
     const float* qp = a.queries + (size_t)q * a.dim;
     const float mag_b = a.q_mag[q];
-    // eight survivors per lane at a time: their records and then their rows' norms (random 4-byte
-    // reads, DRAM latency) are all in flight before the first key is computed
-    for (u32 j0 = 0; j0 < P; j0 += 256) {
-        u64 raw[8];
-        float na[8];
-#pragma unroll
-        for (u32 u = 0; u < 8; u++) {
-            const u32 j = j0 + u * 32 + lane;
-            raw[u] = j < n ? src[j] : 0ull;
+    const float thr = a.q_thr[q];
+    // compact the survivors that pass (NaN scores always do) to the front of the scratch, raw
+    u32 m = 0;
+    for (u32 j0 = 0; j0 < n; j0 += 32) {
+        const u32 j = j0 + lane;
+        u64 raw = 0;
+        bool pass = false;
+        if (j < n) {
+            raw = src[j];
+            const float t = __uint_as_float((u32)raw);
+            pass = !(t < thr);
         }
-#pragma unroll
-        for (u32 u = 0; u < 8; u++) {
-            const u32 j = j0 + u * 32 + lane;
-            na[u] = j < n ? __ldg(a.norms + (u32)(raw[u] >> 32)) : 0.0f;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, pass);
+        if (pass) scratch[m + __popc(bal & ((1u << lane) - 1u))] = raw;
+        m += __popc(bal);
+    }
+    __syncwarp();
+    u32 P = K;
+    while (P < m) P <<= 1;
+    // exact keys, 32 survivors at a time (in place: entry j is read before it is overwritten)
+    for (u32 j0 = 0; j0 < P; j0 += 32) {
+        const u32 j = j0 + lane;
+        u64 key = kKeyMax;
+        if (j < m) {
+            const u64 raw = scratch[j];
+            key = survivor_key(a, raw, __ldg(a.norms + (u32)(raw >> 32)), qp, mag_b);
         }
-#pragma unroll
-        for (u32 u = 0; u < 8; u++) {
-            const u32 j = j0 + u * 32 + lane;
-            if (j < P) scratch[j] = j < n ? survivor_key(a, raw[u], na[u], qp, mag_b) : kKeyMax;
-        }
+        __syncwarp();
+        if (j < P) scratch[j] = key;
     }
     __syncwarp();
     warp_sort_list(scratch, P, lane);
     u64* out = a.cta_keys + (size_t)list * K;
     for (u32 j = lane; j < K; j += 32) out[j] = scratch[j];
+}
+
+// largest finite |a| (norms are >= 0: their bit patterns order like the values)
+__global__ void max_norm_kernel(const float* __restrict__ norms, u32 n, u32* __restrict__ out_bits) {
+    float m = 0.0f;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float v = norms[i];
+        if (v < INFINITY) m = fmaxf(m, v);
+    }
+    for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, d));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));
+}
+
+// fp32 store -> its bf16 shadow in the tensor path's tile layout (rows [row_lo, row_hi), whole 16-byte
+// chunks: thread t owns destination chunk t of the tile range), plus 1/|a| for the filter's score scale.
+__global__ void shadow_from_panels_kernel(const float4* __restrict__ panels, uint4* __restrict__ tiles,
+                                          const float* __restrict__ norms, float* __restrict__ inv_norms,
+                                          u32 row_lo, u32 row_hi, u32 dim, u32 dq, u32 KB) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 row, col;
+    bf16_chunk_coords(t, row_lo >> 6, KB, row, col);
+    if (row >= ((row_hi + 63u) & ~63u)) return;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[e] = 0.0f;
+    // every row of the first tile is (re)converted, also those below row_lo: same values as before
+    if (row < row_hi) {
+        const float4* p = panels + (size_t)(row >> 5) * dq * 32 + (row & 31u);
+        if (col < dim) {  // columns past dim are zero in the panels as well
+            const float4 x = p[(size_t)(col >> 2) * 32];
+            v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+            if (col + 4 < dq * 4) {
+                const float4 y = p[(size_t)((col >> 2) + 1) * 32];
+                v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+            }
+        }
+        if (col == 0) {
+            const float na = norms[row];
+            inv_norms[row] = (na > 0.0f && na < INFINITY) ? __fdiv_rn(1.0f, na) : 0.0f;
+        }
+    }
+    tiles[(size_t)(row_lo >> 6) * KB * 512 + t] = pack8_bf16(v);
 }
 
 #endif  // BSR_TEMPLATES_ONLY

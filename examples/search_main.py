@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """The search phase of the reference's driver (src/main.rs:107-186, SKIP_PROCESS=true) on GPUs.
 
-    python examples/search_main.py [VSTORE_DIR]                     # one rank
-    torchrun --nproc-per-node N examples/search_main.py [VSTORE_DIR]  # one rank per GPU
+    python examples/search_main.py [VSTORE_DIR] [--check]                     # one rank
+    torchrun --nproc-per-node N examples/search_main.py [VSTORE_DIR] [--check]  # one rank per GPU
 
 VSTORE_DIR holds global.parquet and rank_0.parquet as the reference writes them
 (src/mpi_helpers/vectorstore.rs:5-20); without an argument a synthetic JabRef-sized store
 (2 305 x 768, README.md:159 of the reference) is written to a temporary directory first.
-Prints what the reference prints: the top-k list, the accuracy metrics and the timing report."""
+Prints what the reference prints: the top-k list, the accuracy metrics and the timing report.
+With --check root also runs the CPU restatement of the reference (oracle/, test infrastructure) over
+the same Parquet file and prints the GPU-vs-CPU agreement in the same layout: MRR and recall@k of the
+GPU results, and their top-k overlap with the CPU results (src/metrics.rs:21-141)."""
 import os
 import sys
 import tempfile
@@ -32,8 +35,10 @@ def main():
     manager = BenchmarkManager(rank)
     overall = BenchmarkTimer.start("total_execution")                      # main.rs:36
 
-    if len(sys.argv) > 1:
-        vstore_dir = sys.argv[1]
+    check = "--check" in sys.argv
+    argv = [a for a in sys.argv[1:] if a != "--check"]
+    if argv:
+        vstore_dir = argv[0]
     else:
         vstore_dir = os.path.join(tempfile.gettempdir(), "bsr_example_vstore")
         if bsr.is_root(rank):
@@ -65,6 +70,17 @@ def main():
             bsr.print_top_k_results(top)                                   # main.rs:145
             mrr, recall, overlap = bsr.calculate_accuracy_metrics(top, query_idx, top_k)
             print(bsr.format_accuracy_metrics(mrr, recall, overlap, top_k))  # main.rs:151-154
+            if check:
+                from better_search_rag_rust_b200.vectorstore import _read_parquet_rows
+                from oracle import c_oracle as co
+                rows = _read_parquet_rows(os.path.join(vstore_dir, "global.parquet"))
+                q = target.cpu().numpy()
+                ci, cd = co.parallel_top_k_similarity_search(rows, size, top_k, q, n_threads=os.cpu_count() or 1)
+                same = [p[0] for p in top] == ci.tolist() and \
+                    np.asarray([p[1] for p in top], np.float32).view(np.uint32).tolist() == cd.view(np.uint32).tolist()
+                print(f"GPU vs CPU reference path ({size} rank(s)): "
+                      f"{'identical lists (indices and distance bits)' if same else 'LISTS DIFFER'}")
+                print(bsr.agreement_report([q], [[rows[int(i)] for i in ci]], [[rows[p[0]] for p in top]], top_k))
         else:
             print("Error: Failed to compute global top-k results")
     manager.record(metrics_timer.stop())
