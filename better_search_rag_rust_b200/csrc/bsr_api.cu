@@ -954,9 +954,11 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
             if (!fin_configured[s->device & 63]) {
                 CU(cudaFuncSetAttribute(finalize_survivors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(4 * 2 * BSR_MAX_TOP_K * sizeof(u64))));
+                CU(cudaFuncSetAttribute(survivor_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(kThrSmemValues * sizeof(u32))));
                 fin_configured[s->device & 63] = true;
             }
-            survivor_threshold_kernel<<<a.nq_valid, 256, 0, st>>>(a, n_clusters);
+            survivor_threshold_kernel<<<a.nq_valid, 256, kThrSmemValues * sizeof(u32), st>>>(a, n_clusters);
             s->launches++;
             CU(cudaGetLastError());
             finalize_survivors_kernel<<<(lists + wpb - 1) / wpb, wpb * 32, (size_t)wpb * surv_cap * sizeof(u64), st>>>(
@@ -1097,7 +1099,7 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
         a.fin.host_flag = (fuse && nq == 1) ? s->host_flag : nullptr;
         a.fin.flag_value = s->flag_seq;
         a.fin.mb = Mailbox{};
-        if (s->mailbox && K == 32 && nq == 1) a.fin.mb = *s->mailbox;
+        if (s->mailbox && fuse && nq == 1) a.fin.mb = *s->mailbox;
         a.dbg = a.fin.dbg = nullptr;
 #ifdef BSR_TC_TIMELINE
         static unsigned long long* d_dbg = nullptr;
@@ -1675,8 +1677,10 @@ static Mailbox mailbox_for(const bsr_comm* c, u32 seq) {
 // Can this search exchange its candidates through the NVLink mailbox?  Every input is identical on all
 // ranks (arguments, dimension, option), so all ranks take the same path.
 static bool mailbox_usable(const bsr_store* s, const bsr_comm* c, u32 nq, u32 K) {
-    return c->mb_ok && !s->kn.no_mailbox && nq == 1 && K == kMbSlots && !s->kn.scan_ldg &&
-           bulk_stages(s, K, 1) >= 2 && !tensor_eligible(s, 1, K);
+    // K <= 128: the scan's last CTA merges (fused final stage); 32 < K: its shared-memory lists must hold one
+    // list per rank (8 warps' worth at least)
+    return c->mb_ok && !s->kn.no_mailbox && nq == 1 && K <= kMbSlots && (K == 32 || c->n_ranks <= kBulkWarps) &&
+           !s->kn.scan_ldg && !s->kn.no_fuse_wide && bulk_stages(s, K, 1) >= 2 && !tensor_eligible(s, 1, K);
 }
 
 static u32 next_mailbox_seq(bsr_comm* c) {
@@ -1696,7 +1700,7 @@ static int launch_mailbox_only(bsr_store* s, const Mailbox& mb, u32 k, u64* d_ca
     fo.host_flag = host_flag;
     fo.flag_value = flag_value;
     fo.mb = mb;
-    mailbox_only_kernel<<<1, 32, 0, st>>>(fo, k);
+    mailbox_only_kernel<<<1, 256, 0, st>>>(fo, k, bsr_candidate_slots(k));
     s->launches++;
     CU(cudaGetLastError());
     return BSR_OK;

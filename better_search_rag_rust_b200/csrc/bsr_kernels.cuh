@@ -424,16 +424,16 @@ __device__ __forceinline__ u64 ldcg_u64(const u64* p) {
 //   entry = 16 bytes {key, seq}, written with ONE 16-byte store: a peer store is delivered whole, so an
 //   entry whose seq field equals the current search's sequence number carries that search's key -- no
 //   fence, no separate flag (the "LL" protocol of collective libraries).
-//   root's mailbox: [kMbDepth][n_ranks][32] entries; search `seq` uses slot seq % kMbDepth, so a peer
+//   root's mailbox: [kMbDepth][n_ranks][kMbSlots] entries; search `seq` uses slot seq % kMbDepth, so a peer
 //   may run up to kMbDepth searches ahead of root before it has to wait for root's acknowledgement
 //   (root stores the last sequence number it has consumed into every peer's `ack` word).
 // ------------------------------------------------------------------------------------------
 constexpr u32 kMbDepth = 4;
-constexpr u32 kMbSlots = 32;  // top_k <= 32 (one candidate block per rank)
+constexpr u32 kMbSlots = 128;  // entries per rank and search: top_k <= 128 (the reference's own k is 50, src/main.rs:110)
 
 struct Mailbox {
     ulonglong2* send;         // non-root: root's entries for (seq % kMbDepth, my rank) -- PEER memory; else nullptr
-    const ulonglong2* recv;   // root: my entries for seq % kMbDepth, [n_ranks][32] -- local memory; else nullptr
+    const ulonglong2* recv;   // root: my entries for seq % kMbDepth, [n_ranks][kMbSlots] -- local memory; else nullptr
     const u32* ack_local;     // non-root: where root's acknowledgements land (local memory)
     u32* const* ack_remote;   // root: [n_ranks] pointers to the peers' ack words (PEER memory)
     u32* status;              // pinned host word, set to 1 when a wait below gave up
@@ -500,6 +500,52 @@ __device__ __forceinline__ u64 mailbox_exchange32(u64 v, const Mailbox& mb, u32 
     return v;
 }
 
+// The same exchange for 32 < K <= 128, by the whole CTA: `ql[0..K)` (shared memory) holds this rank's
+// final ascending list; `ql` has room for `room` lists of K keys (the per-warp lists it was reduced from).
+// Non-root: send.  Root: the peers' lists land in ql[K..n_ranks*K) as they arrive and the lot is reduced
+// again with cta_merge_lists.  Needs n_ranks <= room (host-checked).  Ends with __syncthreads().
+__device__ __forceinline__ void mailbox_exchange_cta(u64* ql, u32 K, u32 k, const Mailbox& mb) {
+    constexpr long long kGiveUp = 1ll << 33;
+    const u32 tid = threadIdx.x, nt = blockDim.x;
+    if (mb.send) {
+        if (mb.seq > kMbDepth && tid == 0) {  // flow control, see mailbox_exchange32
+            const long long t0 = clock64();
+            while (*reinterpret_cast<const volatile u32*>(mb.ack_local) + kMbDepth < mb.seq) {
+                if (clock64() - t0 > kGiveUp) {
+                    *reinterpret_cast<volatile u32*>(mb.status) = 1;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        for (u32 j = tid; j < K; j += nt) st_volatile_v2(mb.send + j, j < k ? ql[j] : kKeyMax, (u64)mb.seq);
+        __syncthreads();
+        return;
+    }
+    if (!mb.recv) return;
+    const long long t0 = clock64();
+    for (u32 t = tid; t < (mb.n_ranks - 1) * K; t += nt) {
+        const u32 r = 1 + t / K, j = t % K;
+        ulonglong2 e;
+        while (true) {
+            e = ld_volatile_v2(mb.recv + (size_t)r * kMbSlots + j);
+            if (e.y == (u64)mb.seq) break;
+            if (clock64() - t0 > kGiveUp) {
+                *reinterpret_cast<volatile u32*>(mb.status) = 1;
+                e.x = kKeyMax;
+                break;
+            }
+        }
+        ql[(size_t)r * K + j] = e.x;
+    }
+    u32 L = 1;
+    while (L < mb.n_ranks) L <<= 1;
+    for (u32 t = tid + mb.n_ranks * K; t < L * K; t += nt) ql[t] = kKeyMax;  // pad to a power of two of lists
+    __syncthreads();
+    cta_merge_lists(ql, L, K);  // ends with __syncthreads()
+    if (tid > 0 && tid < mb.n_ranks) *reinterpret_cast<volatile u32*>(mb.ack_remote[tid]) = mb.seq;
+}
+
 // Optional outputs of the fused final stage (see scan_epilogue); all indexed by query
 struct FinalOut {
     u32* done_counter;  // zero before the launch; the last CTA to finish resets it
@@ -513,7 +559,7 @@ struct FinalOut {
     // retire and the stream to signal.  nullptr: no flag.
     u32* host_flag;
     u32 flag_value;
-    Mailbox mb;         // cross-rank exchange fused into the last CTA (k <= 32, one query); all-null: none
+    Mailbox mb;         // cross-rank exchange fused into the last CTA (k <= 128, one query); all-null: none
     unsigned long long* dbg;  // debug stamps (see ScanArgs::dbg)
 };
 
@@ -649,6 +695,7 @@ __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta
         for (int q = 0; q < NQ; q++) {
             u64* ql = lists + (size_t)q * W * K;
             cta_merge_lists(ql, W, K);  // ends with __syncthreads()
+            if (NQ == 1) mailbox_exchange_cta(ql, K, k, fo.mb);  // multi-rank: send to root / fold the peers in
             u32 valid = 0;
             for (u32 j = tid; j < K; j += W * 32) {
                 const u64 v = ql[j];
@@ -1321,18 +1368,51 @@ __global__ void __launch_bounds__(32) merge32_kernel(const u64* __restrict__ in,
 // The mailbox exchange for a rank that has nothing of its own to contribute (empty shard, or a local
 // scan that failed: the reference's empty list, metrics.rs:185-191): send an empty list / fold the
 // peers' lists, then publish like the scan's last CTA does.  One warp.
-__global__ void __launch_bounds__(32) mailbox_only_kernel(const FinalOut fo, u32 k) {
-    const int lane = threadIdx.x;
-    const u64 v = mailbox_exchange32(kKeyMax, fo.mb, k, lane);
-    if (fo.keys) fo.keys[lane] = (u32)lane < k ? v : kKeyMax;
-    if (fo.idx) {
-        const bool ok = (u32)lane < k && v != kKeyMax;
-        if ((u32)lane < k) {
-            fo.idx[lane] = ok ? (v & 0xFFFFFFFFull) : 0ull;
-            fo.dist[lane] = ok ? __uint_as_float(bits_from_ordered((u32)(v >> 32))) : 0.0f;
+__global__ void __launch_bounds__(256) mailbox_only_kernel(const FinalOut fo, u32 k, u32 K) {
+    __shared__ u64 ql[8 * 128];  // up to 8 ranks' lists of K <= 128 keys (more ranks: K == 32 only, host-checked)
+    const u32 tid = threadIdx.x;
+    if (K == 32) {
+        if (tid >= 32) return;  // one warp; publish_host_flag's barrier is skipped below for the others
+        const int lane = (int)tid;
+        const u64 v = mailbox_exchange32(kKeyMax, fo.mb, k, lane);
+        if (fo.keys) fo.keys[lane] = (u32)lane < k ? v : kKeyMax;
+        if (fo.idx) {
+            const bool ok = (u32)lane < k && v != kKeyMax;
+            if ((u32)lane < k) {
+                fo.idx[lane] = ok ? (v & 0xFFFFFFFFull) : 0ull;
+                fo.dist[lane] = ok ? __uint_as_float(bits_from_ordered((u32)(v >> 32))) : 0.0f;
+            }
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+            if (lane == 0) fo.count[0] = (u32)__popc(m);
         }
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
-        if (lane == 0) fo.count[0] = (u32)__popc(m);
+        if (fo.host_flag) {
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) *reinterpret_cast<volatile u32*>(fo.host_flag) = fo.flag_value;
+        }
+        return;
+    }
+    for (u32 j = tid; j < K; j += blockDim.x) ql[j] = kKeyMax;
+    __syncthreads();
+    mailbox_exchange_cta(ql, K, k, fo.mb);
+    u32 valid = 0;
+    for (u32 j = tid; j < K; j += blockDim.x) {
+        const u64 v = ql[j];
+        if (fo.keys) fo.keys[j] = j < k ? v : kKeyMax;
+        if (fo.idx && j < k) {
+            const bool ok = v != kKeyMax;
+            fo.idx[j] = ok ? (v & 0xFFFFFFFFull) : 0ull;
+            fo.dist[j] = ok ? __uint_as_float(bits_from_ordered((u32)(v >> 32))) : 0.0f;
+            valid += ok ? 1u : 0u;
+        }
+    }
+    if (fo.idx) {
+        __shared__ u32 s_valid;
+        if (tid == 0) s_valid = 0;
+        __syncthreads();
+        if (valid) atomicAdd(&s_valid, valid);
+        __syncthreads();
+        if (tid == 0) fo.count[0] = s_valid;
     }
     publish_host_flag(fo);
 }

@@ -784,9 +784,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
 // exact top-k; the rest (~98 % of them) are dropped without ever touching their rows again.
 // One CTA per query; radix selection over the order-preserving bit image of t, 32 counting passes over
 // the values held in shared memory (or re-read from the lists when they do not fit).
-constexpr u32 kThrSmemValues = 12000;  // just under the 48 KiB of static shared memory
+constexpr u32 kThrSmemValues = 40960;  // 160 KiB of dynamic shared memory (top-100 on 10 M rows: ~9-12 k values per query)
 __global__ void __launch_bounds__(256) survivor_threshold_kernel(const TensorScanArgs a, u32 n_cta) {
-    __shared__ u32 s_vals[kThrSmemValues];
+    extern __shared__ __align__(16) u32 s_vals[];  // [kThrSmemValues]
     __shared__ u32 s_count[8];
     __shared__ u32 s_total;
     const u32 q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -222,7 +222,7 @@ class BsrComm:
         return out
 
     def uses_mailbox(self) -> bool:
-        """True when single-query top_k <= 32 searches exchange candidates through NVLink peer stores
+        """True when single-query top_k <= 128 searches exchange candidates through NVLink peer stores
         fused into the scan kernel instead of ncclAllGather + a merge launch."""
         yes = C.c_int()
         _lib.check(_lib.lib().bsr_comm_uses_mailbox(self._h, C.byref(yes)))

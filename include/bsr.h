@@ -199,7 +199,7 @@ BSR_API int bsr_comm_destroy(bsr_comm *comm);
  * ranks the outputs are not written (the reference returns None there); they may be NULL.
  * A rank whose local scan fails still joins the exchange with an empty list (the reference's
  * behaviour, metrics.rs:185-191) and returns its error afterwards; the other ranks complete.
- * Single queries with top_k <= 32 skip the collective call altogether when the communicator has a
+ * Single queries with top_k <= 128 skip the collective call altogether when the communicator has a
  * mailbox (bsr_comm_uses_mailbox). */
 BSR_API int bsr_search_parallel(bsr_store *shard, bsr_comm *comm, const float *queries,
                                 uint32_t n_queries, uint32_t top_k, uint64_t *out_idx,
@@ -212,7 +212,7 @@ BSR_API int bsr_search_parallel_device(bsr_store *shard, bsr_comm *comm, const f
                                        uint32_t n_queries, uint32_t top_k, uint64_t *d_candidates,
                                        void *stream);
 
-/* 1 when this communicator exchanges single-query, top_k <= 32 candidates through the NVLink mailbox
+/* 1 when this communicator exchanges single-query, top_k <= 128 candidates through the NVLink mailbox
  * (peer stores from the scan's last CTA into root's HBM, folded in by root's last CTA: one kernel per
  * rank and search, no collective call); 0 when every search uses ncclAllGather + a merge launch
  * (ranks in one process, two ranks on one GPU, no peer access, BSR_NO_MAILBOX set at create time).

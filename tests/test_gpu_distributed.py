@@ -74,10 +74,10 @@ def _worker(rank, size, port, n_rows, k, q_out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("k,n_rows", [(10, 100_003), (32, 20_011), (100, 100_003), (10, 5)])
+@pytest.mark.parametrize("k,n_rows", [(10, 100_003), (32, 20_011), (50, 2_305), (100, 100_003), (200, 30_000), (10, 5), (50, 5)])
 def test_nccl_parallel_search(k, n_rows):
     """Every GPU of the box as one rank: torch's NCCL group, the library's communicator with the NVLink
-    mailbox (k <= 32) and with ncclAllGather, host buffers and device-resident -- all against the
+    mailbox (k <= 128) and with ncclAllGather, host buffers and device-resident -- all against the
     oracle's parallel_top_k_similarity_search.  n_rows = 5 leaves ranks with an empty shard."""
     import torch
     import torch.multiprocessing as mp

@@ -1,5 +1,5 @@
 """Runs the BASELINE.json configurations that fit one GPU and prints one JSON object
-(gpurun_out/r01_configs.json).  Device-side numbers use CUDA events on the launching stream."""
+(gpurun_out/r02_configs.json).  Device-side numbers use CUDA events on the launching stream."""
 import json
 import sys
 import time
@@ -83,7 +83,10 @@ single_query("config4_shard_12.5M_fp32_k10", 12_500_000, 10, reps=50)
 single_query("extra_1M_bf16_k10_exact", 1_000_000, 10, dtype="bf16")
 for k in (1, 50, 100, 256, 1024):
     single_query(f"config5_ksweep_1M_fp32_k{k}", 1_000_000, k, reps=100)
-batches("config5_batch_sweep_1M_fp32_exact_k10", 1_000_000, 10, "f32", [1, 2, 4, 8, 64, 256])
-batches("config5_batch_sweep_1M_bf16_tensor_k10", 1_000_000, 10, "bf16", [32, 128, 1024, 4096])
+single_query("config0c_2305_fp32_k50_reference_store", 2305, 50, reps=500)
+batches("config5_batch_sweep_1M_fp32_k10", 1_000_000, 10, "f32", [1, 2, 4, 8, 16, 32, 64, 256, 1024, 4096])
+batches("config5_batch_sweep_1M_bf16_k10", 1_000_000, 10, "bf16", [1, 8, 32, 128, 1024, 4096])
+batches("config5_k_sweep_1M_bf16_256_queries", 1_000_000, 1024, "bf16", [256])
 batches("config2_10M_bf16_tensor_k100", 10_000_000, 100, "bf16", [128, 1024])
-json.dump(out, open("gpurun_out/r01_configs.json", "w"), indent=1)
+batches("config2b_10M_fp32_tensor_k100", 10_000_000, 100, "f32", [1024])
+json.dump(out, open("gpurun_out/r02_configs.json", "w"), indent=1)

@@ -1,11 +1,14 @@
 """BASELINE.json configs[4]: k sweep 1-1024 and query-batch sweep 1-4096 on N x B200 (one process per
 GPU, launched with torch.distributed.run).  The store is 100 M x 768 rows at N = 8 (12.5 M rows per
-GPU; --rows-per-gpu to change), resident once as fp32 (exact path) and once as bf16 (tcgen05 path).
+GPU; --rows-per-gpu to change), resident once as fp32 and once as bf16.  Batches of 32 queries and
+more run on the tcgen05 filter + exact rescoring (fp32 stores through their bf16 shadow), smaller ones
+on the exact scan; every result is the exact scan's, bit for bit.
 
 Every measurement is one `bsr_search_parallel` call per rank (C ABI, host query buffers in, the
-root's host top-k out: scan -> ncclAllGather of the candidate slots -> merge on the root), timed on
-the host around the collective call after a barrier, max over ranks.  Rank 0 prints one JSON
-object and writes it to gpurun_out/r01_sweeps_n<N>.json."""
+root's host top-k out: scan -> candidate exchange (NVLink mailbox for one query with k <= 128, else
+ncclAllGather + merge launch) -> final list on root), timed on the host around the collective call
+after a barrier, max over ranks.  Rank 0 prints one JSON object and writes it to
+gpurun_out/r02_sweeps_n<N>.json."""
 import argparse
 import json
 import os
@@ -26,8 +29,7 @@ DIM = 768
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows-per-gpu", type=int, default=12_500_000)
-    ap.add_argument("--max-exact-batch", type=int, default=256,
-                    help="largest batch timed on the exact fp32 path (8 queries share one pass)")
+    ap.add_argument("--max-batch", type=int, default=4096)
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -56,7 +58,8 @@ def main():
         return float(t.item()) / reps, res
 
     out = {"n_gpus": world, "rows_per_gpu": n, "rows_total": n * world, "dim": DIM,
-           "path": "bsr_search_parallel (C ABI, host buffers; scan -> ncclAllGather -> merge on root)"}
+           "path": "bsr_search_parallel (C ABI, host buffers; scan -> candidate exchange -> final list on root)",
+           "mailbox": comm.uses_mailbox()}
     rng = np.random.default_rng(1)
 
     def queries(nq, first):
@@ -93,26 +96,33 @@ def main():
         sweep = []
         sizes = (1, 2, 8, 64, 256, 1024, 4096)
         for nq in sizes:
-            if dtype == "f32" and nq > args.max_exact_batch:
+            if nq > args.max_batch:
                 continue
             q = queries(nq, row0)
             reps = max(1, min(20, 64 // nq))
             s, res = timed(lambda: comm.search(eng, q, 10), reps)
             if rank == 0:
                 idx, dst, cnt = res
-                assert int(idx[0, 0]) == 0 and abs(float(dst[0, 0])) <= 2e-6
+                assert int(idx[0, 0]) == 0 and float(dst[0, 0]) == 0.0
             e = {"queries": nq, "ms_per_batch": s * 1e3, "queries_per_s": nq / s}
-            if dtype == "bf16" and nq >= 32:
+            if nq >= 32:
                 e["TFLOPs_aggregate"] = 2.0 * n * world * DIM * nq / s / 1e12
             else:
                 e["aggregate_GBps_per_query_pass"] = bytes_total * nq / s / 1e9
             sweep.append(e)
-        out[f"batch_sweep_{dtype}_k10" + ("_exact" if dtype == "f32" else "_exact_below_32_tcgen05_above")] = sweep
+        out[f"batch_sweep_{dtype}_k10_exact_scan_below_32_tcgen05_filter_above"] = sweep
+        if dtype == "bf16":
+            sweep = []
+            for k in (100, 1024):
+                q = queries(1024, row0)
+                s, res = timed(lambda: comm.search(eng, q, k), 1)
+                sweep.append({"k": k, "queries": 1024, "ms_per_batch": s * 1e3, "queries_per_s": 1024 / s})
+            out["k_sweep_bf16_1024_queries"] = sweep
         store.close()
 
     if rank == 0:
         os.makedirs("gpurun_out", exist_ok=True)
-        with open(f"gpurun_out/r01_sweeps_n{world}.json", "w") as f:
+        with open(f"gpurun_out/r02_sweeps_n{world}.json", "w") as f:
             json.dump(out, f, indent=1)
         print(json.dumps(out))
     dist.barrier()
