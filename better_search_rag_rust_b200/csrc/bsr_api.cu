@@ -157,8 +157,9 @@ struct bsr_store {
     // set by bsr_search around ONE search_device_impl call: the host query to pass in the kernel's
     // parameter block, and the pinned-host flag the last CTA publishes behind the results
     const float* param_query = nullptr;
-    u32* host_flag = nullptr;
-    u32 flag_seq = 0;
+    u64* host_ll = nullptr;   // FinalOut::host_ll of the launch being set up
+    u32 ll_k = 0;
+    u32 ll_seq = 0;
     const Mailbox* mailbox = nullptr;  // set by bsr_search_parallel around one fused launch
 
     u64 launches = 0;
@@ -212,6 +213,7 @@ static int ensure_pinned(bsr_store* s, size_t bytes) {
     s->h_pinned = nullptr;
     s->h_pinned_bytes = 0;
     CU(cudaMallocHost(&s->h_pinned, bytes));
+    memset(s->h_pinned, 0, bytes);
     s->h_pinned_bytes = bytes;
     return BSR_OK;
 }
@@ -686,14 +688,17 @@ static u32 bulk_max_qb(const bsr_store* s, u32 K) {
     return 1;
 }
 
-template <int QB, bool BF16, int W = kBulkWarps>
+template <int QB, bool BF16, int W = kBulkWarps, bool K32 = false>
 static int launch_scan_bulk_t(bsr_store* s, const ScanArgs& a, unsigned grid, u32 stages, u32 active_warps,
                               cudaStream_t st, u32* panel_ticket = nullptr) {
+    if constexpr (QB == 1 && !K32) {  // top_k <= 32, one query: the K-specialised instantiation
+        if (a.k_pad == 32) return launch_scan_bulk_t<1, BF16, W, true>(s, a, grid, stages, active_warps, st, panel_ticket);
+    }
     static thread_local bool configured[64] = {false};
     if (!configured[s->device & 63]) {
         cudaFuncAttributes fa;
-        CU(cudaFuncGetAttributes(&fa, scan_topk_bulk_kernel<QB, BF16, W>));
-        CU(cudaFuncSetAttribute(scan_topk_bulk_kernel<QB, BF16, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CU(cudaFuncGetAttributes(&fa, scan_topk_bulk_kernel<QB, BF16, W, K32>));
+        CU(cudaFuncSetAttribute(scan_topk_bulk_kernel<QB, BF16, W, K32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(s->smem_optin - fa.sharedSizeBytes)));
         configured[s->device & 63] = true;
     }
@@ -709,7 +714,7 @@ static int launch_scan_bulk_t(bsr_store* s, const ScanArgs& a, unsigned grid, u3
         memcpy(ba.qparam, s->param_query, (size_t)s->dim * sizeof(float));
         ba.qparam_mag = host_query_magnitude(s->param_query, s->dim);
     }
-    scan_topk_bulk_kernel<QB, BF16, W>
+    scan_topk_bulk_kernel<QB, BF16, W, K32>
         <<<grid, W * 32, bulk_smem_bytes(s, a.k_pad, stages, QB, active_warps, W), st>>>(ba);
     s->launches++;
     CU(cudaGetLastError());
@@ -1096,8 +1101,9 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
         a.fin.idx = d_idx ? d_idx + (size_t)q * k : nullptr;
         a.fin.dist = d_idx ? d_dist + (size_t)q * k : nullptr;
         a.fin.count = d_idx ? d_count + q : nullptr;
-        a.fin.host_flag = (fuse && nq == 1) ? s->host_flag : nullptr;
-        a.fin.flag_value = s->flag_seq;
+        a.fin.host_ll = (fuse && nq == 1) ? s->host_ll : nullptr;
+        a.fin.ll_k = s->ll_k;
+        a.fin.ll_seq = s->ll_seq;
         a.fin.mb = Mailbox{};
         if (s->mailbox && fuse && nq == 1) a.fin.mb = *s->mailbox;
         a.dbg = a.fin.dbg = nullptr;
@@ -1153,9 +1159,9 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
             for (int i = 0; i < 11; i++) fprintf(stderr, " [%s %lld]", names[i], h_dbg[i] ? (long long)(h_dbg[i] - h_dbg[0]) : -1LL);
             if (h_dbg[13] > h_dbg[12] && h_dbg[4] > h_dbg[0])
                 fprintf(stderr, " [SM clock %.0f MHz over the panel loop]", (double)(h_dbg[13] - h_dbg[12]) * 1e3 / (double)(h_dbg[4] - h_dbg[0]));
-            fprintf(stderr, "\n  chunk wait->ready:");
+            fprintf(stderr, "\n  cta0 warp0 chunks, SM cycles since the first wait (wait->ready):");
             for (int i = 0; i < 24; i++)
-                fprintf(stderr, " %lld->%lld", (long long)(h_dbg[16 + 2 * i] - h_dbg[0]), (long long)(h_dbg[17 + 2 * i] - h_dbg[0]));
+                fprintf(stderr, " %u->%u", (unsigned)(h_dbg[16 + 2 * i] - h_dbg[16]), (unsigned)(h_dbg[17 + 2 * i] - h_dbg[16]));
             fprintf(stderr, "\n");
         }
 #endif
@@ -1233,24 +1239,52 @@ extern "C" int bsr_unpack_device(bsr_store* s, const uint64_t* d_cand, uint32_t 
     return mark_busy(s, st);
 }
 
-// Host side of FinalOut::host_flag: wait until the last CTA has published `seq` behind the results.
-// Polls the pinned word; every ~20 us also asks the stream, so a failed launch or a faulting kernel
+// Host side of FinalOut::host_ll: poll the self-validating result words of search `seq` in the pinned
+// block and unpack them.  The count word is written last by the kernel but every word is checked on its
+// own.  Every ~1 000 polls the stream is asked as well, so a failed launch or a faulting kernel
 // surfaces as an error instead of a hang.
-static int wait_host_flag(bsr_store* s, const volatile u32* flag, u32 seq) {
-    for (u32 spins = 0;; spins++) {
-        if (*flag == seq) return BSR_OK;
-        if ((spins & 0x3FF) == 0x3FF) {
-            cudaError_t e = cudaStreamQuery(s->stream);
-            if (e == cudaSuccess) {
-                if (*flag == seq) return BSR_OK;
-                return fail(BSR_ERR_CUDA, "bsr_search: the scan finished without publishing its result");
+static int wait_host_ll(bsr_store* s, const volatile u64* ll, u32 seq, u32 k, uint64_t* out_idx, float* out_dist,
+                        uint32_t* out_count) {
+    auto wait_word = [&](u32 i, u32* value) -> int {
+        for (u32 spins = 0;; spins++) {
+            const u64 w = ll[i];
+            if ((u32)(w >> 32) == seq) {
+                *value = (u32)w;
+                return BSR_OK;
             }
-            if (e != cudaErrorNotReady) return fail(BSR_ERR_CUDA, "bsr_search: %s", cudaGetErrorString(e));
-        }
+            if ((spins & 0x3FF) == 0x3FF) {
+                cudaError_t e = cudaStreamQuery(s->stream);
+                if (e == cudaSuccess) {
+                    const u64 w2 = ll[i];
+                    if ((u32)(w2 >> 32) == seq) {
+                        *value = (u32)w2;
+                        return BSR_OK;
+                    }
+                    return fail(BSR_ERR_CUDA, "search: the scan finished without publishing its result");
+                }
+                if (e != cudaErrorNotReady) return fail(BSR_ERR_CUDA, "search: %s", cudaGetErrorString(e));
+            }
 #if defined(__x86_64__) || defined(__i386__)
-        __builtin_ia32_pause();
+            __builtin_ia32_pause();
 #endif
+        }
+    };
+    u32 count = 0;
+    TRY(wait_word(2 * k, &count));
+    for (u32 j = 0; j < k; j++) {
+        u32 v = 0;
+        TRY(wait_word(j, &v));
+        out_idx[j] = v;
+        TRY(wait_word(k + j, &v));
+        memcpy(&out_dist[j], &v, sizeof(float));
     }
+    if (out_count) *out_count = count;
+    return BSR_OK;
+}
+
+static u32 next_ll_seq(bsr_store* s) {
+    s->ll_seq = s->ll_seq + 1 ? s->ll_seq + 1 : 1;  // never 0: a fresh pinned block reads 0
+    return s->ll_seq;
 }
 
 extern "C" int bsr_search(bsr_store* s, const float* queries, uint32_t nq, uint32_t k,
@@ -1267,8 +1301,8 @@ extern "C" int bsr_search(bsr_store* s, const float* queries, uint32_t nq, uint3
     // search is at most one H2D copy, the kernels, one D2H copy
     const size_t rbytes = ibytes + dbytes + cbytes;
     const size_t off_r = (qbytes + 15) & ~(size_t)15;
-    const size_t off_flag = (off_r + rbytes + 63) & ~(size_t)63;
-    TRY(ensure_pinned(s, off_flag + 64));
+    const size_t off_ll = (off_r + rbytes + 63) & ~(size_t)63;  // one-launch searches: (2k + 1) self-validating words
+    TRY(ensure_pinned(s, off_ll + (2 * (size_t)k + 1) * sizeof(u64)));
     TRY(ensure(s->d_queries, qbytes));
     TRY(ensure(s->d_cand, (size_t)nq * K * sizeof(u64)));
     TRY(ensure(s->d_result, rbytes));
@@ -1290,12 +1324,13 @@ extern "C" int bsr_search(bsr_store* s, const float* queries, uint32_t nq, uint3
                             s->dim <= kParamQueryMax && !s->kn.no_param_query && bulk_stages(s, K, 1) >= 2 &&
                             !tensor_eligible(s, 1, K);
     char* r = direct ? h + off_r : (char*)s->d_result.p;
-    volatile u32* flag = (volatile u32*)(h + off_flag);
+    volatile u64* ll = (volatile u64*)(h + off_ll);
     if (one_launch) {
         s->param_query = queries;
-        s->host_flag = (u32*)flag;
-        s->flag_seq = s->flag_seq + 1 ? s->flag_seq + 1 : 1;  // never 0
-        *flag = 0;  // whatever an earlier call left in this word of the shared pinned block
+        s->host_ll = (u64*)ll;
+        s->ll_k = k;
+        next_ll_seq(s);
+        for (u32 i = 0; i < 2 * k + 1; i++) ll[i] = 0;  // whatever an earlier call left in these words of the shared block
     } else {
         memcpy(h, queries, qbytes);
     }
@@ -1322,10 +1357,11 @@ extern "C" int bsr_search(bsr_store* s, const float* queries, uint32_t nq, uint3
         }
     }
     if (!one_launch) CU(cudaMemcpyAsync(s->d_queries.p, h, qbytes, cudaMemcpyHostToDevice, s->stream));
-    int rc = search_device_impl(s, (const float*)s->d_queries.p, nq, k, (u64*)s->d_cand.p, (u64*)r,
-                                (float*)(r + ibytes), (u32*)(r + ibytes + dbytes), s->stream);
+    int rc = search_device_impl(s, (const float*)s->d_queries.p, nq, k, (u64*)s->d_cand.p,
+                                one_launch ? nullptr : (u64*)r, (float*)(r + ibytes), (u32*)(r + ibytes + dbytes),
+                                s->stream);
     s->param_query = nullptr;
-    s->host_flag = nullptr;
+    s->host_ll = nullptr;
     for (size_t i = 0; i < degenerate.size() && rc == BSR_OK; i++) {
         const u32 q = degenerate[i];
         rc = ensure(s->d_query1, (size_t)s->dim * sizeof(float));
@@ -1343,12 +1379,13 @@ extern "C" int bsr_search(bsr_store* s, const float* queries, uint32_t nq, uint3
     s->tensor_min_batch = saved_min_batch;
     TRY(rc);
     if (one_launch) {
-        TRY(wait_host_flag(s, flag, s->flag_seq));
+        TRY(wait_host_ll(s, ll, s->ll_seq, k, out_idx, out_dist, out_count));
         // the kernel may still be retiring; the next call on this handle is stream-ordered behind it
-    } else {
-        if (!direct) CU(cudaMemcpyAsync(h + off_r, r, rbytes, cudaMemcpyDeviceToHost, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
+        mark_idle(s);
+        return BSR_OK;
     }
+    if (!direct) CU(cudaMemcpyAsync(h + off_r, r, rbytes, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
     mark_idle(s);
     memcpy(out_idx, h + off_r, ibytes);
     memcpy(out_dist, h + off_r + ibytes, dbytes);
@@ -1690,15 +1727,13 @@ static u32 next_mailbox_seq(bsr_comm* c) {
 
 // A rank with nothing to scan (empty shard, or a local failure) still takes part: one warp sends an
 // empty list / folds the peers' lists and publishes.
-static int launch_mailbox_only(bsr_store* s, const Mailbox& mb, u32 k, u64* d_cand, u64* d_idx, float* d_dist,
-                               u32* d_count, u32* host_flag, u32 flag_value, cudaStream_t st) {
+static int launch_mailbox_only(bsr_store* s, const Mailbox& mb, u32 k, u64* d_cand, u64* host_ll, u32 ll_k, u32 ll_seq,
+                               cudaStream_t st) {
     FinalOut fo{};
     fo.keys = d_cand;
-    fo.idx = d_idx;
-    fo.dist = d_dist;
-    fo.count = d_count;
-    fo.host_flag = host_flag;
-    fo.flag_value = flag_value;
+    fo.host_ll = host_ll;
+    fo.ll_k = ll_k;
+    fo.ll_seq = ll_seq;
     fo.mb = mb;
     mailbox_only_kernel<<<1, 256, 0, st>>>(fo, k, bsr_candidate_slots(k));
     s->launches++;
@@ -1725,12 +1760,12 @@ extern "C" int bsr_search_parallel(bsr_store* s, bsr_comm* c, const float* queri
     const size_t ibytes = (size_t)nq * k * sizeof(u64), dbytes = (size_t)nq * k * sizeof(float),
                  cbytes = (size_t)nq * sizeof(u32);
     const size_t rbytes = ibytes + dbytes + cbytes, off_r = (qbytes + 15) & ~(size_t)15;
-    const size_t off_flag = (off_r + rbytes + 63) & ~(size_t)63;
+    const size_t off_flag = (off_r + rbytes + 63) & ~(size_t)63;  // mailbox path: (2k + 1) self-validating result words
     const size_t cand_bytes = (size_t)nq * K * sizeof(u64);
     // the two buffers the exchange itself needs; without them this rank cannot take part at all
     TRY(ensure(s->d_cand, cand_bytes));
     TRY(ensure(s->d_gather, cand_bytes * c->n_ranks + cand_bytes));
-    TRY(ensure_pinned(s, off_flag + 64));
+    TRY(ensure_pinned(s, off_flag + (2 * (size_t)k + 1) * sizeof(u64)));
     TRY(order_after_previous(s, s->stream));
     char* h = (char*)s->h_pinned;
 
@@ -1739,13 +1774,10 @@ extern "C" int bsr_search_parallel(bsr_store* s, bsr_comm* c, const float* queri
         const u32 seq = next_mailbox_seq(c);
         const Mailbox mb = mailbox_for(c, seq);
         *c->h_status = 0;
-        volatile u32* flag = (volatile u32*)(h + off_flag);
-        *flag = 0;
-        s->flag_seq = s->flag_seq + 1 ? s->flag_seq + 1 : 1;
-        char* r = h + off_r;  // nq == 1: results go straight to the pinned block
-        u64* d_idx = root ? (u64*)r : nullptr;
-        float* d_dist = root ? (float*)(r + ibytes) : nullptr;
-        u32* d_count = root ? (u32*)(r + ibytes + dbytes) : nullptr;
+        volatile u64* ll = (volatile u64*)(h + off_flag);
+        const u32 ll_k = root ? k : 0;  // the other ranks only signal completion (the count word)
+        const u32 ll_seq = next_ll_seq(s);
+        for (u32 i = 0; i < 2 * ll_k + 1; i++) ll[i] = 0;
         int local_rc = BSR_OK;
         if (s->n_rows != 0) {
             const bool in_params = s->dim <= kParamQueryMax && !s->kn.no_param_query;
@@ -1759,20 +1791,22 @@ extern "C" int bsr_search_parallel(bsr_store* s, bsr_comm* c, const float* queri
             }
             if (local_rc == BSR_OK) {
                 s->param_query = in_params ? queries : nullptr;
-                s->host_flag = (u32*)flag;
+                s->host_ll = (u64*)ll;
+                s->ll_k = ll_k;
                 s->mailbox = &mb;
-                local_rc = search_device_impl(s, (const float*)s->d_queries.p, nq, k, (u64*)s->d_cand.p, d_idx, d_dist,
-                                              d_count, s->stream);
+                local_rc = search_device_impl(s, (const float*)s->d_queries.p, nq, k, (u64*)s->d_cand.p, nullptr, nullptr,
+                                              nullptr, s->stream);
                 s->param_query = nullptr;
-                s->host_flag = nullptr;
+                s->host_ll = nullptr;
                 s->mailbox = nullptr;
             }
         }
         char local_err[sizeof g_err];
         if (local_rc != BSR_OK) memcpy(local_err, g_err, sizeof g_err);
         if (s->n_rows == 0 || local_rc != BSR_OK)
-            TRY(launch_mailbox_only(s, mb, k, (u64*)s->d_cand.p, d_idx, d_dist, d_count, (u32*)flag, s->flag_seq, s->stream));
-        TRY(wait_host_flag(s, flag, s->flag_seq));
+            TRY(launch_mailbox_only(s, mb, k, (u64*)s->d_cand.p, (u64*)ll, ll_k, ll_seq, s->stream));
+        u32 cnt = 0;
+        TRY(wait_host_ll(s, ll, ll_seq, ll_k, out_idx, out_dist, &cnt));
         mark_idle(s);
         if (local_rc != BSR_OK) {
             memcpy(g_err, local_err, sizeof g_err);
@@ -1780,11 +1814,7 @@ extern "C" int bsr_search_parallel(bsr_store* s, bsr_comm* c, const float* queri
         }
         CHECK(*c->h_status == 0, BSR_ERR_CUDA,
               "bsr_search_parallel: a rank did not deliver its candidates (mailbox wait gave up)");
-        if (root) {
-            memcpy(out_idx, r, ibytes);
-            memcpy(out_dist, r + ibytes, dbytes);
-            memcpy(out_count, r + ibytes + dbytes, cbytes);
-        }
+        if (root) *out_count = cnt;
         return BSR_OK;
     }
 
@@ -1878,7 +1908,7 @@ extern "C" int bsr_search_parallel_device(bsr_store* s, bsr_comm* c, const float
         char local_err[sizeof g_err];
         if (rc != BSR_OK) memcpy(local_err, g_err, sizeof g_err);
         if (s->n_rows == 0 || rc != BSR_OK)
-            TRY(launch_mailbox_only(s, mb, k, (u64*)d_candidates, nullptr, nullptr, nullptr, nullptr, 0, st));
+            TRY(launch_mailbox_only(s, mb, k, (u64*)d_candidates, nullptr, 0, 0, st));
         TRY(mark_busy(s, st));
         if (rc != BSR_OK) memcpy(g_err, local_err, sizeof g_err);
         return rc;

@@ -220,8 +220,9 @@ __device__ __forceinline__ void warp_list_insert(u64* list, int k, u64 x, int la
 __device__ __forceinline__ void warp_sort_list(u64* list, u32 K, int lane) {
     for (u32 size = 2; size <= K; size <<= 1) {
         for (u32 d = size >> 1; d >= 1; d >>= 1) {
+            const u32 ld = 31 - __clz(d);  // d is a power of two: no integer division in the index arithmetic
             for (u32 t = lane; t < (K >> 1); t += 32) {
-                const u32 lo = ((t / d) * 2 * d) + (t % d), hi = lo + d;
+                const u32 lo = ((t >> ld) << (ld + 1)) + (t & (d - 1)), hi = lo + d;
                 const bool asc = (lo & size) == 0;
                 const u64 x = list[lo], y = list[hi];
                 if ((x > y) == asc) {
@@ -553,22 +554,35 @@ struct FinalOut {
     u64* idx;           // [nq][k]  or nullptr
     float* dist;        // [nq][k]
     u32* count;         // [nq]
-    // When idx/dist/count live in pinned host memory (bsr_search, small results): after they are
-    // written the last CTA publishes `flag_value` here (same pinned block), system-fenced behind
-    // them, and the host picks the result up by polling instead of waiting for the whole grid to
-    // retire and the stream to signal.  nullptr: no flag.
-    u32* host_flag;
-    u32 flag_value;
+    // One-launch searches (bsr_search / bsr_search_parallel, one query): the result goes to pinned host
+    // memory as self-validating 8-byte words -- (sequence number << 32) | value -- which the host polls:
+    //   host_ll[0 .. ll_k)        global row indices (they fit 32 bits, include/bsr.h)
+    //   host_ll[ll_k .. 2 ll_k)   distance bit patterns
+    //   host_ll[2 ll_k]           count
+    // An 8-byte store arrives whole, so a word whose upper half is this search's sequence number carries
+    // this search's value: no system-scope fence (a ~2 us stall in the last CTA: it waits for every
+    // posted PCIe write to be acknowledged), no waiting for the grid to retire and the stream to signal.
+    // ll_k == 0 (a non-root rank of a multi-rank search): only the count word, as a completion signal.
+    // nullptr: results go to idx / dist / count.
+    u64* host_ll;
+    u32 ll_k;
+    u32 ll_seq;
     Mailbox mb;         // cross-rank exchange fused into the last CTA (k <= 128, one query); all-null: none
     unsigned long long* dbg;  // debug stamps (see ScanArgs::dbg)
 };
 
-// end of the fused final stage: every result write of this CTA is ordered before the flag
-__device__ __forceinline__ void publish_host_flag(const FinalOut& fo) {
-    if (!fo.host_flag) return;  // kernel-uniform
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) *reinterpret_cast<volatile u32*>(fo.host_flag) = fo.flag_value;
+__device__ __forceinline__ void ll_store(u64* p, u32 seq, u32 value) {
+    *reinterpret_cast<volatile u64*>(p) = ((u64)seq << 32) | (u64)value;
+}
+// slot j of the final list (key v) and, from one thread, the count
+__device__ __forceinline__ void ll_publish_entry(const FinalOut& fo, u32 j, u64 v) {
+    if (j >= fo.ll_k) return;
+    const bool ok = v != kKeyMax;
+    ll_store(fo.host_ll + j, fo.ll_seq, ok ? (u32)v : 0u);
+    ll_store(fo.host_ll + fo.ll_k + j, fo.ll_seq, ok ? bits_from_ordered((u32)(v >> 32)) : 0u);
+}
+__device__ __forceinline__ void ll_publish_count(const FinalOut& fo, u32 count) {
+    ll_store(fo.host_ll + 2 * fo.ll_k, fo.ll_seq, count);
 }
 
 #ifdef BSR_TC_TIMELINE
@@ -715,9 +729,21 @@ __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta
                 if (tid == 0) fo.count[q] = s_valid[0] + s_valid[1] + s_valid[2] + s_valid[3];
                 __syncthreads();
             }
+            if (NQ == 1 && fo.host_ll) {
+                u32 v_ok = 0;
+                for (u32 j = tid; j < K; j += W * 32) {
+                    const u64 v = ql[j];
+                    ll_publish_entry(fo, j, v);
+                    v_ok += (j < fo.ll_k && v != kKeyMax) ? 1u : 0u;
+                }
+                const u32 wsum = __reduce_add_sync(0xFFFFFFFFu, v_ok);
+                __shared__ u32 s_ll_valid[4];
+                if (warp < 4 && lane == 0) s_ll_valid[warp] = wsum;
+                __syncthreads();
+                if (tid == 0) ll_publish_count(fo, s_ll_valid[0] + s_ll_valid[1] + s_ll_valid[2] + s_ll_valid[3]);
+            }
         }
         if (tid == 0) *fo.done_counter = 0;
-        publish_host_flag(fo);
         BSR_STAMP(fo.dbg, tid == 0, 10);
         return;
     }
@@ -763,9 +789,13 @@ __device__ __forceinline__ void scan_epilogue(u64* lists, u32 K, u32 k, u64* cta
             const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
             if (lane == 0) fo.count[q] = (u32)__popc(m);
         }
+        if (NQ == 1 && fo.host_ll) {
+            ll_publish_entry(fo, (u32)lane, v);
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, (u32)lane < fo.ll_k && v != kKeyMax);
+            if (lane == 0) ll_publish_count(fo, (u32)__popc(m));
+        }
     }
     if (tid == 0) *fo.done_counter = 0;
-    publish_host_flag(fo);
     BSR_STAMP(fo.dbg, tid == 0, 10);
 }
 
@@ -971,7 +1001,10 @@ constexpr u32 kParamQueryMax = 768;
 // arithmetic is the same sequential binary32 fold over the widened bf16 values.
 // W = warps per CTA: 8 (default), or 16 for small stores, where a second round of panels on a few
 // warps would otherwise double the (latency-bound) run time.
-template <int QB, bool BF16, int W = kBulkWarps>
+// K32: the launch has k_pad == 32 (top_k <= 32, the headline case): every K > 32 path -- batched
+// inserts, shared-memory list merges, the wide last-CTA fold -- is compiled out, which cuts the kernel
+// to a fraction of its size (a small store's launch is largely instruction-cache misses otherwise).
+template <int QB, bool BF16, int W = kBulkWarps, bool K32 = false>
 __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const __grid_constant__ BulkScanArgs ba) {
     const ScanArgs& a = ba.s;
     constexpr int CH = kChunkQuads;                    // fp32: column-quads per 4 KiB chunk
@@ -980,7 +1013,7 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const __grid_
 #ifdef BSR_TC_TIMELINE
     if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[12] = (unsigned long long)clock64();
 #endif
-    const u32 dq = a.dq, S = ba.stages, K = a.k_pad;
+    const u32 dq = a.dq, S = ba.stages, K = K32 ? 32u : a.k_pad;
     // [ring: active_warps*S*4KiB | queries: dq*QB*16, sq[j*QB + b] = column-quad j of query b (one
     //  address register per quad, the query index is an immediate offset) | lists: QB*W*K*8 |
     //  mbarriers: W*S*8]
@@ -1013,6 +1046,10 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const __grid_
     // consumed it is at most ONE panel ahead of the consumer -- which is how the consumer learns its
     // next panel in the dynamic deal.  Lane 0 draws the ticket for the panel after `ipanel` as soon as
     // `ipanel` is known: the atomic's round trip is hidden behind a whole panel of requests.
+#ifdef BSR_TC_TIMELINE
+    __shared__ u32 s_tl[48];
+    if (threadIdx.x < 48) s_tl[threadIdx.x] = 0;
+#endif
     __shared__ u32 s_zero[32];  // see draw_ticket
     if (tid < 32) s_zero[tid] = 0;
     u32 ipanel = panel0, ici = 0, islot = 0, inext = 0;
@@ -1097,9 +1134,13 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const __grid_
 #pragma unroll
             for (int b = 0; b < QB; b++) acc[b] = 0.0f;
         }
-        BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0 && c < 24, 16 + 2 * c);
+#ifdef BSR_TC_TIMELINE  // per-chunk SM-clock stamps of CTA 0 / warp 0, kept in shared memory until the loop is over
+        if (a.dbg && blockIdx.x == 0 && tid == 0 && c < 24) s_tl[2 * c] = (u32)clock64();
+#endif
         mbar_wait(bar0 + stage * 8, parity);
-        BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0 && c < 24, 17 + 2 * c);
+#ifdef BSR_TC_TIMELINE
+        if (a.dbg && blockIdx.x == 0 && tid == 0 && c < 24) s_tl[2 * c + 1] = (u32)clock64();
+#endif
         BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0 && c == 0, 3);
         if (BF16) {
             // my row inside the 4 KiB half tile: atom lane/8, row lane%8; chunk c at (c ^ row%8)
@@ -1133,7 +1174,20 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const __grid_
 #pragma unroll
                     for (int b = 0; b < QB; b++) {
                         const float4 qa = sq[(q0i + 2 * cc) * QB + b], qb2 = sq[(q0i + 2 * cc + 1) * QB + b];
-                        acc[b] = dot8_seq_bf16(acc[b], v, qa, qb2);
+                        if (QB == 1) {
+                            // one query: the eight products first, then the eight dependent adds (see the
+                            // fp32 path: same values, better use of the adds' latency slots)
+                            const float p0 = __fmul_rn(bf16_lo(v.x), qa.x), p1 = __fmul_rn(bf16_hi(v.x), qa.y);
+                            const float p2 = __fmul_rn(bf16_lo(v.y), qa.z), p3 = __fmul_rn(bf16_hi(v.y), qa.w);
+                            const float p4 = __fmul_rn(bf16_lo(v.z), qb2.x), p5 = __fmul_rn(bf16_hi(v.z), qb2.y);
+                            const float p6 = __fmul_rn(bf16_lo(v.w), qb2.z), p7 = __fmul_rn(bf16_hi(v.w), qb2.w);
+                            float t = acc[b];
+                            t = __fadd_rn(t, p0); t = __fadd_rn(t, p1); t = __fadd_rn(t, p2); t = __fadd_rn(t, p3);
+                            t = __fadd_rn(t, p4); t = __fadd_rn(t, p5); t = __fadd_rn(t, p6); t = __fadd_rn(t, p7);
+                            acc[b] = t;
+                        } else {
+                            acc[b] = dot8_seq_bf16(acc[b], v, qa, qb2);
+                        }
                     }
                 }
             }
@@ -1172,6 +1226,28 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const __grid_
                             qsq[b] = sq4_seq(qsq[b], q);
                         }
                     }
+                } else if (QB == 1) {
+                    // One query: the only chain is the row's own 32 dependent adds.  All 32 products first
+                    // (independent, separately rounded as the reference's are), then the adds in column
+                    // order: the scheduler fills the adds' latency slots with the multiplies and the
+                    // shared-memory reads instead of alternating dependent FMUL/FADD pairs -- what bounds a
+                    // warp that has its scheduler to itself (small stores) or shares it with one other.
+                    float4 pr[CH];
+#pragma unroll
+                    for (int u = 0; u < CH; u++) {
+                        const float4 q = sq[j0 + u];
+                        pr[u].x = __fmul_rn(v[u].x, q.x);
+                        pr[u].y = __fmul_rn(v[u].y, q.y);
+                        pr[u].z = __fmul_rn(v[u].z, q.z);
+                        pr[u].w = __fmul_rn(v[u].w, q.w);
+                    }
+#pragma unroll
+                    for (int u = 0; u < CH; u++) {
+                        acc[0] = __fadd_rn(acc[0], pr[u].x);
+                        acc[0] = __fadd_rn(acc[0], pr[u].y);
+                        acc[0] = __fadd_rn(acc[0], pr[u].z);
+                        acc[0] = __fadd_rn(acc[0], pr[u].w);
+                    }
                 } else {
 #pragma unroll
                     for (int u = 0; u < CH; u++) {
@@ -1183,10 +1259,21 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const __grid_
 #pragma unroll
                     for (int b = 0; b < QB; b++) {
                         if ((maybe_mask >> b) & 1u) {
-                            bool d = false;
+                            // bitwise-equal columns never differ (differs4_fast): one OR-reduction over the
+                            // chunk, branch-free; the subtract-compare pass only if some bit differs
+                            u32 x = 0;
 #pragma unroll
-                            for (int u = 0; u < CH; u++) d |= differs4_fast(v[u], sq[(j0 + u) * QB + b]);
-                            if (d) maybe_mask &= ~(1u << b);
+                            for (int u = 0; u < CH; u++) {
+                                const float4 q = sq[(j0 + u) * QB + b];
+                                x |= (__float_as_uint(v[u].x) ^ __float_as_uint(q.x)) | (__float_as_uint(v[u].y) ^ __float_as_uint(q.y)) |
+                                     (__float_as_uint(v[u].z) ^ __float_as_uint(q.z)) | (__float_as_uint(v[u].w) ^ __float_as_uint(q.w));
+                            }
+                            if (x) {
+                                bool d = false;
+#pragma unroll
+                                for (int u = 0; u < CH; u++) d |= differs4(v[u], sq[(j0 + u) * QB + b]);
+                                if (d) maybe_mask &= ~(1u << b);
+                            }
                         }
                     }
                 }
@@ -1263,7 +1350,10 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const __grid_
     }
     BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 4);
 #ifdef BSR_TC_TIMELINE
-    if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[13] = (unsigned long long)clock64();
+    if (a.dbg && blockIdx.x == 0 && tid == 0) {
+        a.dbg[13] = (unsigned long long)clock64();
+        for (int i = 0; i < 48; i++) a.dbg[16 + i] = s_tl[i];
+    }
 #endif
 #pragma unroll
     for (int b = 0; b < QB; b++) top[b].finish(lane);
@@ -1316,8 +1406,9 @@ __global__ void pack_sort_lists_kernel(const u64* __restrict__ idx, const float*
     __syncthreads();
     for (u32 size = 2; size <= K; size <<= 1) {
         for (u32 d = size >> 1; d >= 1; d >>= 1) {
+            const u32 ld = 31 - __clz(d);
             for (u32 t = threadIdx.x; t < (K >> 1); t += blockDim.x) {
-                const u32 lo = ((t / d) * 2 * d) + (t % d), hi = lo + d;
+                const u32 lo = ((t >> ld) << (ld + 1)) + (t & (d - 1)), hi = lo + d;
                 const bool asc = (lo & size) == 0;
                 const u64 x = buf[lo], y = buf[hi];
                 if ((x > y) == asc) {
@@ -1372,7 +1463,7 @@ __global__ void __launch_bounds__(256) mailbox_only_kernel(const FinalOut fo, u3
     __shared__ u64 ql[8 * 128];  // up to 8 ranks' lists of K <= 128 keys (more ranks: K == 32 only, host-checked)
     const u32 tid = threadIdx.x;
     if (K == 32) {
-        if (tid >= 32) return;  // one warp; publish_host_flag's barrier is skipped below for the others
+        if (tid >= 32) return;  // one warp
         const int lane = (int)tid;
         const u64 v = mailbox_exchange32(kKeyMax, fo.mb, k, lane);
         if (fo.keys) fo.keys[lane] = (u32)lane < k ? v : kKeyMax;
@@ -1385,10 +1476,10 @@ __global__ void __launch_bounds__(256) mailbox_only_kernel(const FinalOut fo, u3
             const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
             if (lane == 0) fo.count[0] = (u32)__popc(m);
         }
-        if (fo.host_flag) {
-            __threadfence_system();
-            __syncwarp();
-            if (lane == 0) *reinterpret_cast<volatile u32*>(fo.host_flag) = fo.flag_value;
+        if (fo.host_ll) {
+            ll_publish_entry(fo, (u32)lane, v);
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, (u32)lane < fo.ll_k && v != kKeyMax);
+            if (lane == 0) ll_publish_count(fo, (u32)__popc(m));
         }
         return;
     }
@@ -1414,7 +1505,19 @@ __global__ void __launch_bounds__(256) mailbox_only_kernel(const FinalOut fo, u3
         __syncthreads();
         if (tid == 0) fo.count[0] = s_valid;
     }
-    publish_host_flag(fo);
+    if (fo.host_ll) {
+        __shared__ u32 s_ll;
+        if (tid == 0) s_ll = 0;
+        __syncthreads();
+        u32 v_ok = 0;
+        for (u32 j = tid; j < K; j += blockDim.x) {
+            ll_publish_entry(fo, j, ql[j]);
+            v_ok += (j < fo.ll_k && ql[j] != kKeyMax) ? 1u : 0u;
+        }
+        if (v_ok) atomicAdd(&s_ll, v_ok);
+        __syncthreads();
+        if (tid == 0) ll_publish_count(fo, s_ll);
+    }
 }
 
 // candidates[q][K] -> idx[q][k] (u64, as the reference's usize), dist[q][k], count[q]
