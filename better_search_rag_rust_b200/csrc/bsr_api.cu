@@ -886,15 +886,10 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
     const u32 QS = C * kTcQ;  // queries per launch
     const u32 stages = tensor_stages(s, mode), stage_kb = tensor_stage_kb(s, mode);
     const size_t smem = tensor_smem_bytes(stage_kb, stages, mode);
-    TRY(ensure(s->cta_keys, (size_t)nq * n_clusters * K * sizeof(u64)));
     const size_t gm_bytes = (size_t)QS * ((k + kTcN - 1) / kTcN) * kTcN * sizeof(u32);
     TRY(ensure(s->d_gtau, gm_bytes));
     const size_t surv_bytes = (size_t)QS * n_clusters * 2 * surv_cap * sizeof(u64);
     TRY(ensure(s->d_surv, surv_bytes + (size_t)QS * n_clusters * sizeof(u32) + 2 * QS * sizeof(float)));
-    const u32 max_per_cta = std::max<u32>(2, kMergeMaxKeys / K);
-    const size_t inter = (size_t)nq * ((n_clusters + max_per_cta - 1) / max_per_cta) * K * sizeof(u64);
-    TRY(ensure(s->merge_a, inter));
-    TRY(ensure(s->merge_b, inter));
     if (s->metric == BSR_DOT && !s->ones.p) {
         TRY(ensure(s->ones, kTcN * sizeof(float)));
         float h_ones[kTcN];
@@ -913,12 +908,11 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
         a.norms = s->norms;
         a.inv_norms = s->inv_norms;
         a.queries = d_queries + (size_t)q0 * s->dim;
-        a.cta_keys = (u64*)s->cta_keys.p + (size_t)q0 * n_clusters * K;
+        a.cta_keys = nullptr;
         a.g_gm = (u32*)s->d_gtau.p;
         a.survivors = (u64*)s->d_surv.p;
         a.surv_count = (u32*)((char*)s->d_surv.p + surv_bytes);
         a.q_mag = (float*)(a.surv_count + (size_t)QS * n_clusters);
-        a.q_thr = a.q_mag + QS;
         a.nq_valid = std::min(QS, nq - q0);
         a.n_rows = (u32)s->n_rows;
         a.n_tiles = n_tiles;
@@ -954,20 +948,15 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
         else if (mode == 1) TRY(launch_tensor<1>(s, a, grid, smem, st));
         else TRY(launch_tensor<0>(s, a, grid, smem, st));
         {
-            const u32 lists = a.nq_valid * n_clusters, wpb = 4;  // 4 warps x surv_cap keys of sort scratch per CTA
-            static thread_local bool fin_configured[64] = {false};
-            if (!fin_configured[s->device & 63]) {
-                CU(cudaFuncSetAttribute(finalize_survivors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(4 * 2 * BSR_MAX_TOP_K * sizeof(u64))));
-                CU(cudaFuncSetAttribute(survivor_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(kThrSmemValues * sizeof(u32))));
-                fin_configured[s->device & 63] = true;
+            // per query: final threshold, exact keys of the survivors near it, the query's final list
+            const size_t sel_smem = (size_t)K * sizeof(u64) + std::max((size_t)kThrSmemValues * sizeof(u32), (size_t)kSelChunk * sizeof(u64));
+            static thread_local bool sel_configured[64] = {false};
+            if (!sel_configured[s->device & 63]) {
+                CU(cudaFuncSetAttribute(select_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(BSR_MAX_TOP_K * sizeof(u64) + kThrSmemValues * sizeof(u32))));
+                sel_configured[s->device & 63] = true;
             }
-            survivor_threshold_kernel<<<a.nq_valid, 256, kThrSmemValues * sizeof(u32), st>>>(a, n_clusters);
-            s->launches++;
-            CU(cudaGetLastError());
-            finalize_survivors_kernel<<<(lists + wpb - 1) / wpb, wpb * 32, (size_t)wpb * surv_cap * sizeof(u64), st>>>(
-                a, n_clusters);
+            select_rescore_kernel<<<a.nq_valid, kSelThreads, sel_smem, st>>>(a, n_clusters, d_cand + (size_t)q0 * K);
             s->launches++;
             CU(cudaGetLastError());
         }
@@ -1008,7 +997,6 @@ static int search_tensor(bsr_store* s, const float* d_queries, u32 nq, u32 k, u6
     }
     CU(cudaEventRecord(s->ev_scan1, st));
     s->scan_timed = true;
-    TRY(merge_tree(s, (const u64*)s->cta_keys.p, n_clusters, nq, K, k, K, (size_t)n_clusters * K, d_cand, st));
     if (d_idx) {
         unpack_kernel<<<nq, 128, 0, st>>>(d_cand, K, k, d_idx, d_dist, d_count);
         s->launches++;

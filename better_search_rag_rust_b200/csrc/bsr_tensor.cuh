@@ -75,12 +75,11 @@ struct TensorScanArgs {
     const float* norms;          // |a| per row
     const float* inv_norms;      // 1/|a| per row (0 where |a| is 0, inf or NaN)
     const float* queries;        // [nq_valid][dim] binary32, device
-    u64* cta_keys;               // [nq_valid][n_clusters][k_pad]
+    u64* cta_keys;               // unused (per-cluster candidate lists of earlier versions)
     u32* g_gm;                   // [64*T][128*C] global class maxima (ordered-float bits), 0 before the launch
     u64* survivors;              // [128*C][n_clusters][2 * kTcSurvivorCap] raw (row, score) pairs
     u32* surv_count;             // [128*C][n_clusters] survivors per (query, cluster)
     float* q_mag;                // [128*C] |b| of the queries as given (written by cluster 0)
-    float* q_thr;                // [128*C] final filter threshold per query (survivor_threshold_kernel)
     u32 nq_valid;                // <= 128 * cluster size
     u32 n_rows, n_tiles, KB, dim, k, k_pad, row_base, stages;
     u32 stage_kb;                // 64-column blocks per ring stage (<= kTcStageKB)
@@ -759,7 +758,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
             }
             if (tid == 0) BSR_TL(sq, 7);
         }
-        // exact keys + sort of the survivors happen in finalize_survivors_kernel (fully parallel)
+        // exact keys + selection of the survivors happen in select_rescore_kernel (one CTA per query)
         if (active) {
             a.surv_count[(size_t)q * n_clusters + cluster_id] = surv_cnt;
             if (cluster_id == 0) a.q_mag[q] = mag_b_exact;
@@ -778,45 +777,88 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_topk_bf16_tensor_kernel(co
 }
 
 #ifndef BSR_TEMPLATES_ONLY
-// Per query, after the scan: the k-th largest filter score t among ALL its survivors (every cluster's
-// list) certifies k distinct rows at least that good -- a far tighter bound than the running one the scan
-// pruned with (which sits near rank kc * H(kc)).  Only survivors within the margin of it can be in the
-// exact top-k; the rest (~98 % of them) are dropped without ever touching their rows again.
-// One CTA per query; radix selection over the order-preserving bit image of t, 32 counting passes over
-// the values held in shared memory (or re-read from the lists when they do not fit).
-constexpr u32 kThrSmemValues = 40960;  // 160 KiB of dynamic shared memory (top-100 on 10 M rows: ~9-12 k values per query)
-__global__ void __launch_bounds__(256) survivor_threshold_kernel(const TensorScanArgs a, u32 n_cta) {
-    extern __shared__ __align__(16) u32 s_vals[];  // [kThrSmemValues]
-    __shared__ u32 s_count[8];
-    __shared__ u32 s_total;
+// ascending bitonic sort of P (power of two) keys in shared memory by the whole CTA
+__device__ __forceinline__ void cta_sort_keys(u64* buf, u32 P) {
+    for (u32 size = 2; size <= P; size <<= 1) {
+        for (u32 d = size >> 1; d >= 1; d >>= 1) {
+            const u32 ld = 31 - __clz(d);
+            for (u32 t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                const u32 lo = ((t >> ld) << (ld + 1)) + (t & (d - 1)), hi = lo + d;
+                const bool asc = (lo & size) == 0;
+                const u64 x = buf[lo], y = buf[hi];
+                if ((x > y) == asc) {
+                    buf[lo] = y;
+                    buf[hi] = x;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Per query, after the scan (one CTA per query of the launch):
+//  1. the k-th largest filter score t among ALL the query's survivors (every cluster's list) certifies
+//     k distinct rows at least that good -- a far tighter bound than the running one the scan pruned
+//     with (which sits near rank kc * H(kc)).  Radix selection over the order-preserving bit image of
+//     t: 32 counting passes over the values held in shared memory (re-read from the lists when they do
+//     not fit).
+//  2. only survivors within the margin of that bound (~2 % of them; NaN scores always) can be in the
+//     exact top-k: they are collected, get their exact key (the reference's distance over the stored
+//     row), are sorted and folded into the query's running best K -- in chunks of kSelChunk, so that
+//     any number of them (a query without a usable direction keeps every survivor) is handled.
+//  3. the K best keys ARE the query's final candidate list: no per-cluster lists, no merge tree.
+// Dynamic shared memory: [running K keys | union{values for step 1, chunk of step 2}].
+constexpr u32 kThrSmemValues = 24576;  // 96 KiB: two CTAs per SM (top-100 on 10 M rows: ~9-12 k values per query)
+constexpr u32 kSelChunk = 2048;        // >= BSR_MAX_TOP_K padded (1024): a chunk's best K merge with the running K
+constexpr u32 kSelThreads = 512;
+constexpr u32 kSelWarps = kSelThreads / 32;
+__global__ void __launch_bounds__(kSelThreads) select_rescore_kernel(const TensorScanArgs a, u32 n_cta, u64* out_keys) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    const u32 K = a.k_pad;
+    u64* running = reinterpret_cast<u64*>(sel_smem);              // [K]
+    u64* chunk = running + K;                                      // [kSelChunk], contiguous with `running`
+    u32* s_vals = reinterpret_cast<u32*>(running + K);             // [kThrSmemValues], dead before `chunk` is used
+    __shared__ u32 s_count[kSelWarps];
+    __shared__ u32 s_off[512];                                     // list offsets (n_cta <= 148 today)
+    __shared__ u32 s_n;
     const u32 q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 cap = a.surv_cap;
     const u64* base = a.survivors + (size_t)q * n_cta * (2 * (size_t)cap);
     const u32* counts = a.surv_count + (size_t)q * n_cta;
-    if (tid == 0) s_total = 0;
-    __syncthreads();
-    // gather the ordered images (a NaN score certifies nothing: image 0, below every number)
-    for (u32 l = 0; l < n_cta; l++) {
-        const u32 n = min(counts[l], cap);
-        if (tid == 0) s_total += n;  // running offset, advanced by one thread per list
-        __syncthreads();
-        const u32 off = s_total - n;
-        for (u32 j = tid; j < n; j += 256) {
-            const float t = __uint_as_float((u32)base[(size_t)l * (2 * (size_t)cap) + j]);
-            if (off + j < kThrSmemValues) s_vals[off + j] = (t == t) ? f32_ordered(t) : 0u;
+    const float* qp = a.queries + (size_t)q * a.dim;
+    const float mag_b = a.q_mag[q];
+
+    for (u32 j = tid; j < K; j += kSelThreads) running[j] = kKeyMax;
+    if (tid == 0) {  // exclusive prefix of the list lengths
+        u32 acc = 0;
+        for (u32 l = 0; l < n_cta; l++) {
+            if (l < 512) s_off[l] = acc;
+            acc += min(counts[l], cap);
         }
-        __syncthreads();
+        s_n = acc;
     }
-    const u32 total = s_total;
-    const bool in_smem = total <= kThrSmemValues;
+    __syncthreads();
+    const u32 total = s_n;
+    const bool in_smem = total <= kThrSmemValues && n_cta <= 512;
+    // ---- step 1: the k-th largest score ---------------------------------------------------------
+    if (in_smem) {  // one warp per list: no barrier while gathering
+        for (u32 l = warp; l < n_cta; l += kSelThreads / 32) {
+            const u32 n = min(counts[l], cap), off = s_off[l];
+            for (u32 j = lane; j < n; j += 32) {
+                const float t = __uint_as_float((u32)base[(size_t)l * (2 * (size_t)cap) + j]);
+                s_vals[off + j] = (t == t) ? f32_ordered(t) : 0u;  // a NaN score certifies nothing: below every number
+            }
+        }
+    }
+    __syncthreads();
     auto count_ge = [&](u32 x) -> u32 {
         u32 c = 0;
         if (in_smem) {
-            for (u32 j = tid; j < total; j += 256) c += s_vals[j] >= x ? 1u : 0u;
+            for (u32 j = tid; j < total; j += kSelThreads) c += s_vals[j] >= x ? 1u : 0u;
         } else {
             for (u32 l = 0; l < n_cta; l++) {
                 const u32 n = min(counts[l], cap);
-                for (u32 j = tid; j < n; j += 256) {
+                for (u32 j = tid; j < n; j += kSelThreads) {
                     const float t = __uint_as_float((u32)base[(size_t)l * (2 * (size_t)cap) + j]);
                     c += ((t == t) ? f32_ordered(t) : 0u) >= x ? 1u : 0u;
                 }
@@ -828,75 +870,104 @@ __global__ void __launch_bounds__(256) survivor_threshold_kernel(const TensorSca
         __syncthreads();
         u32 sum = 0;
 #pragma unroll
-        for (int w = 0; w < 8; w++) sum += s_count[w];
+        for (u32 w = 0; w < kSelWarps; w++) sum += s_count[w];
         return sum;
     };
     float thr = -INFINITY;
-    if (count_ge(1u) >= a.k) {  // at least k survivors with a number for a score
+    const u32 n_numbers = count_ge(1u);
+    if (n_numbers >= a.k) {  // at least k survivors with a number for a score
         u32 ans = 0;
         for (int bit = 31; bit >= 0; bit--) {
             const u32 cand = ans | (1u << bit);
             if (count_ge(cand) >= a.k) ans = cand;
         }
         const float kth = f32_from_ordered(ans);  // k-th largest score
-        const float mag_b = a.q_mag[q];
         thr = kth - a.margin * mag_b - 1e-6f * fabsf(kth);
         if (!(mag_b >= 1e-6f) || !(mag_b < INFINITY)) thr = -INFINITY;  // no usable direction: every survivor is rescored
     }
-    if (tid == 0) a.q_thr[q] = thr;
-}
+    // how many survivors pass (t >= thr, and every NaN score): usually a few hundred -> one chunk, collected
+    // without a single barrier
+    const u32 n_pass = (thr == -INFINITY ? n_numbers : count_ge(f32_ordered(thr))) + (total - n_numbers);
+    __syncthreads();  // s_vals is dead from here on: `chunk` takes its place
 
-// One warp per (query, cluster) survivor list: the survivors that pass the query's final threshold get
-// their exact key (the reference's distance over the stored row, one survivor per lane), the keys are
-// sorted and the best k_pad written as an ascending candidate list.  Dynamic shared memory: surv_cap
-// keys of scratch per warp.
-__global__ void __launch_bounds__(128) finalize_survivors_kernel(const TensorScanArgs a, u32 n_cta) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const u32 cap = a.surv_cap;
-    u64* scratch = reinterpret_cast<u64*>(smem_raw) + (size_t)warp * cap;
-    const u32 list = blockIdx.x * (blockDim.x >> 5) + warp;  // = q * n_cta + cta
-    if (list >= a.nq_valid * n_cta) return;
-    const u32 q = list / n_cta;
-    const u32 K = a.k_pad;
-    const u32 n = min(a.surv_count[list], cap);
-    const u64* src = a.survivors + (size_t)list * (2 * (size_t)cap);
-    const float* qp = a.queries + (size_t)q * a.dim;
-    const float mag_b = a.q_mag[q];
-    const float thr = a.q_thr[q];
-    // compact the survivors that pass (NaN scores always do) to the front of the scratch, raw
-    u32 m = 0;
-    for (u32 j0 = 0; j0 < n; j0 += 32) {
-        const u32 j = j0 + lane;
-        u64 raw = 0;
-        bool pass = false;
-        if (j < n) {
-            raw = src[j];
-            const float t = __uint_as_float((u32)raw);
-            pass = !(t < thr);
+    // ---- step 2: exact keys of the survivors that pass, folded into the running best K ------------
+    auto process_chunk = [&](u32 n) {  // chunk[0..n) raw survivors -> running = K best of running U chunk
+        u32 P = K;
+        while (P < n) P <<= 1;  // <= kSelChunk
+        for (u32 j = tid; j < P; j += kSelThreads) {
+            u64 key = kKeyMax;
+            if (j < n) {
+                const u64 raw = chunk[j];
+                key = survivor_key(a, raw, __ldg(a.norms + (u32)(raw >> 32)), qp, mag_b);
+            }
+            chunk[j] = key;  // entry j is read and written by the same thread
         }
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, pass);
-        if (pass) scratch[m + __popc(bal & ((1u << lane) - 1u))] = raw;
-        m += __popc(bal);
-    }
-    __syncwarp();
-    u32 P = K;
-    while (P < m) P <<= 1;
-    // exact keys, 32 survivors at a time (in place: entry j is read before it is overwritten)
-    for (u32 j0 = 0; j0 < P; j0 += 32) {
-        const u32 j = j0 + lane;
-        u64 key = kKeyMax;
-        if (j < m) {
-            const u64 raw = scratch[j];
-            key = survivor_key(a, raw, __ldg(a.norms + (u32)(raw >> 32)), qp, mag_b);
+        __syncthreads();
+        cta_sort_keys(chunk, P);
+        cta_merge_lists(running, 2, K);  // lists {running, chunk[0..K)} are contiguous; ends with __syncthreads()
+    };
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    if (n_pass <= kSelChunk) {
+        for (u32 l = warp; l < n_cta; l += kSelWarps) {
+            const u32 n = min(counts[l], cap);
+            for (u32 j0 = 0; j0 < n; j0 += 32) {
+                const u32 j = j0 + lane;
+                u64 raw = 0;
+                bool pass = false;
+                if (j < n) {
+                    raw = base[(size_t)l * (2 * (size_t)cap) + j];
+                    const float t = __uint_as_float((u32)raw);
+                    pass = !(t < thr);
+                }
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, pass);
+                u32 off = 0;
+                if (lane == 0 && bal) off = atomicAdd(&s_n, (u32)__popc(bal));
+                off = __shfl_sync(0xFFFFFFFFu, off, 0);
+                if (pass) chunk[off + __popc(bal & ((1u << lane) - 1u))] = raw;
+            }
         }
-        __syncwarp();
-        if (j < P) scratch[j] = key;
+    } else
+    for (u32 l0 = 0; l0 < n_cta; l0 += kSelWarps) {  // a round of lists at a time, one warp each
+        const u32 l = l0 + warp;
+        const u32 n = l < n_cta ? min(counts[l], cap) : 0u;
+        u32 n_max = n;  // the longest of the eight lists bounds the number of rounds (warp-uniform per warp, CTA-uniform below)
+        for (u32 j0 = 0;; j0 += 32) {
+            // CTA-uniform loop: every warp takes part in the barriers until all eight lists are exhausted
+            const u32 j = j0 + lane;
+            u64 raw = 0;
+            bool pass = false;
+            if (j < n) {
+                raw = base[(size_t)l * (2 * (size_t)cap) + j];
+                const float t = __uint_as_float((u32)raw);
+                pass = !(t < thr);
+            }
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, pass);
+            u32 off = 0;
+            if (lane == 0 && bal) off = atomicAdd(&s_n, (u32)__popc(bal));
+            off = __shfl_sync(0xFFFFFFFFu, off, 0);
+            if (pass) chunk[off + __popc(bal & ((1u << lane) - 1u))] = raw;  // room: at most 256 appends per round, see below
+            const bool more = __syncthreads_or(j0 + 32 < n_max);
+            // a full round of warps adds at most kSelThreads entries: process before the next one could overflow
+            if (s_n > kSelChunk - kSelThreads) {
+                const u32 cnt = s_n;
+                __syncthreads();
+                process_chunk(cnt);
+                if (tid == 0) s_n = 0;
+                __syncthreads();
+            }
+            if (!more) break;
+        }
     }
-    __syncwarp();
-    warp_sort_list(scratch, P, lane);
-    u64* out = a.cta_keys + (size_t)list * K;
-    for (u32 j = lane; j < K; j += 32) out[j] = scratch[j];
+    __syncthreads();
+    if (s_n) {
+        const u32 cnt = s_n;
+        __syncthreads();
+        process_chunk(cnt);
+    }
+    // ---- step 3: the query's final list ----------------------------------------------------------
+    u64* out = out_keys + (size_t)q * K;
+    for (u32 j = tid; j < K; j += kSelThreads) out[j] = j < a.k ? running[j] : kKeyMax;  // slots past top_k are published empty
 }
 
 // largest finite |a| (norms are >= 0: their bit patterns order like the values)
