@@ -473,7 +473,7 @@ def run_b200(args):
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                "kernel": "scan_topk_bulk_kernel<1,false,8> (fused cosine scan + top-k), rank 0",
+                "kernel": "scan_topk_bulk_kernel<1,false,8,true> (fused cosine scan + top-k, k <= 32 instantiation), rank 0",
                 "algorithmic_bytes_per_launch": m["scan_bytes"],
                 "avg_launch_ms": avg_scan_ms, "launches_timed": m["n_scans"],
                 "kernel_share_of_step": avg_scan_ms / (m["ms_dev"] / m["steps"]),

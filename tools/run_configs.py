@@ -39,6 +39,8 @@ def single_query(name, n, k, dtype="f32", reps=200, cpu=False):
     ms = timed(lambda: eng.search_candidates(q, k, out=cand), reps)
     scan_ms, n_scans = st.scan_profile()
     st.set_profiling(False)
+    for _ in range(5):  # first calls allocate the pinned result block and the device scratch
+        eng.local_top_k(q_np, k)
     t0 = time.perf_counter()
     for _ in range(reps):
         idx, dist, cnt = eng.local_top_k(q_np, k)
