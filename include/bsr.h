@@ -19,10 +19,10 @@
  *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
  *     BSR_ERR_CUDA.
  *
- * Results are bit-identical to the reference's CPU arithmetic (src/metrics.rs:143-165): the
- * scan keeps the reference's strict left-to-right binary32 sums (no FMA contraction), so
- * distances match bit for bit and ties resolve as the reference's stable sorts do (ascending
- * global row index).
+ * Results are bit-identical to the reference's CPU arithmetic (src/metrics.rs:143-165) on every
+ * path -- single queries, query batches, tensor-core batches, one rank or many: the reference's
+ * strict left-to-right binary32 sums are kept (no FMA contraction), so distances match bit for bit
+ * and ties resolve as the reference's stable sorts do (ascending global row index).
  */
 #ifndef BSR_B200_H
 #define BSR_B200_H
@@ -220,11 +220,15 @@ BSR_API int bsr_search_parallel_device(bsr_store *shard, bsr_comm *comm, const f
  * be set identically on every rank. */
 BSR_API int bsr_comm_uses_mailbox(const bsr_comm *comm, int *yes);
 
-/* BF16 stores only: query batches of at least `min_batch` queries (default 32) are scanned on the
- * tensor cores (tcgen05, queries in tensor memory).  That path is not bit-exact: the tensor core
- * accumulates the (exact) bf16 products in a different order and truncates, so distances agree
- * with the exact path to 2e-6 (4e-6 for rows nearly parallel to the query).  0 disables it: every search then uses the exact scan.  Needs dim <= 768 and
- * top_k <= 128; other shapes always use the exact scan. */
+/* Query batches of at least `min_batch` queries (default 8; 0 = never) are scanned on the tensor
+ * cores (tcgen05, queries in tensor memory) -- as a FILTER: bf16-rounded queries against the bf16
+ * rows (an fp32 store gets a bf16 shadow copy, +50 % HBM, built on the first such batch), a certified
+ * bound with a margin of twice the worst-case rounding gap, and every survivor's distance recomputed
+ * with the reference's arithmetic over the stored row and the query as given.  Results are
+ * bit-identical to the exact scan's; only the time differs.  Needs dim <= 768; other shapes always
+ * use the exact scan.  Queries without a usable direction (zero, denormal-small, NaN or inf magnitude)
+ * are answered by the exact scan (bsr_search sorts them out; with device-resident queries they stay
+ * correct but slow their launch). */
 BSR_API int bsr_store_set_tensor_min_batch(bsr_store *store, uint32_t min_batch);
 
 /* Ablation switches and test hooks, per handle (DESIGN.md lists them).  Defaults are the measured
