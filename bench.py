@@ -369,6 +369,7 @@ def run_b200(args):
             return comm.search(eng, q_np, k)     # bsr_search_parallel: one C-ABI call per rank
 
         # ---- device-resident region: `value` and the roofline --------------------------------
+        fence()  # every rank's shard is resident before the first collective search (ranks build at their own pace)
         for _ in range(warmup):
             step_device()
         fence()

@@ -430,6 +430,10 @@ __device__ __forceinline__ u64 ldcg_u64(const u64* p) {
 //   (root stores the last sequence number it has consumed into every peer's `ack` word).
 // ------------------------------------------------------------------------------------------
 constexpr u32 kMbDepth = 4;
+// A wait inside a kernel ends after this many SM cycles (~35 s at 1.95 GHz) with an error status: long
+// enough for any skew between the ranks' calls (a collective waits for its slowest caller), short enough
+// that a dead rank becomes an error on the others and never an unbounded spin on the GPU.
+constexpr long long kMbGiveUpCycles = 1ll << 36;
 constexpr u32 kMbSlots = 128;  // entries per rank and search: top_k <= 128 (the reference's own k is 50, src/main.rs:110)
 
 struct Mailbox {
@@ -453,9 +457,9 @@ __device__ __forceinline__ void st_volatile_v2(ulonglong2* p, u64 x, u64 y) {
 // One warp; lane i holds the i-th key of this rank's final (ascending) list.  Non-root: send it.
 // Root: fold every peer's list in as it arrives and acknowledge.  Returns the list to publish.
 // A rank that never delivers (it died, or the caller broke the collective contract) ends the wait after
-// ~4 s of SM clock with *status = 1; the host turns that into an error.
+// kMbGiveUpCycles with *status = 1; the host turns that into an error.
 __device__ __forceinline__ u64 mailbox_exchange32(u64 v, const Mailbox& mb, u32 k, int lane) {
-    constexpr long long kGiveUp = 1ll << 33;
+    constexpr long long kGiveUp = kMbGiveUpCycles;
     if (mb.send) {
         if (mb.seq > kMbDepth) {  // flow control: root must be done with the slot's previous use
             const long long t0 = clock64();
@@ -506,7 +510,7 @@ __device__ __forceinline__ u64 mailbox_exchange32(u64 v, const Mailbox& mb, u32 
 // Non-root: send.  Root: the peers' lists land in ql[K..n_ranks*K) as they arrive and the lot is reduced
 // again with cta_merge_lists.  Needs n_ranks <= room (host-checked).  Ends with __syncthreads().
 __device__ __forceinline__ void mailbox_exchange_cta(u64* ql, u32 K, u32 k, const Mailbox& mb) {
-    constexpr long long kGiveUp = 1ll << 33;
+    constexpr long long kGiveUp = kMbGiveUpCycles;
     const u32 tid = threadIdx.x, nt = blockDim.x;
     if (mb.send) {
         if (mb.seq > kMbDepth && tid == 0) {  // flow control, see mailbox_exchange32
