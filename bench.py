@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run oracle check (profiling runs)")
     ap.add_argument("--no-extra", action="store_true", help="skip the 1 M-row extra measurement")
+    ap.add_argument("--no-sweeps", action="store_true", help="skip the k / batch sweeps on the 1 M-row extra store")
     ap.add_argument("--exchange", choices=["auto", "nccl"], default="auto",
                     help="cross-rank candidate exchange of the e2e leg: library default, or ncclAllGather only")
     return ap.parse_args()
@@ -333,7 +334,7 @@ def run_b200(args):
     sampler = ClockSampler(local)
     sampler.start()
 
-    def measure(n: int, n_steps: int, check: bool) -> dict:
+    def measure(n: int, n_steps: int, check: bool, sweep: bool = False) -> dict:
         """Both timed regions (device-resident and end to end) on an n-row shard per GPU, then the
         parity check of the complete top-k against the oracle."""
         store = bsr.GpuVectorstore(None, True, device=local, row_base=rank * n, dim=DIM, capacity_rows=n)
@@ -403,7 +404,44 @@ def run_b200(args):
             exchange = ("NVLink mailbox: peer stores from each scan's last CTA into root's HBM, folded in by root's "
                         "last CTA (one kernel per rank and query)" if comm.uses_mailbox() and args.exchange != "nccl"
                         else "ncclAllGather of the candidate slots + merge launch on root")
-        out = {"exchange": exchange, "n": n, "steps": n_steps, "ms_dev": ms_dev, "launches": launches, "scan_ms": scan_ms,
+        # ---- BASELINE.json configs[4] in small: k sweep and query-batch sweep, end to end ---------------
+        sweeps = None
+        if sweep:
+            sweeps = {"path": "bsr_search / bsr_search_parallel (C ABI, host buffers), host-timed, max over ranks; "
+                              "queries/s against the whole store", "k_sweep_single_query": [], "batch_sweep_k10": []}
+            rng = np.random.default_rng(11)
+
+            def timed_e2e(fn, reps):
+                fn()
+                fence()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    r = fn()
+                s_ = reduce_ranks(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
+                return s_ / reps, r
+
+            def search(qs, kk):
+                return eng.local_top_k(qs, kk) if world == 1 else comm.search(eng, qs, kk)
+
+            for kk in (1, 50, 100, 1024):
+                sec, r = timed_e2e(lambda: search(q_np, kk), 20)
+                if rank == 0:
+                    assert int(r[0][0, 0]) == 0 and float(r[1][0, 0]) == 0.0 and int(r[2][0]) == kk
+                sweeps["k_sweep_single_query"].append({"k": kk, "ms_per_query": sec * 1e3, "queries_per_s": 1.0 / sec})
+            for nq in (8, 64, 256, 1024):
+                qs = rng.uniform(-1, 1, size=(nq, DIM)).astype(np.float32)
+                qs[0] = q_np[0]
+                if world > 1:  # every rank must pass the same queries
+                    t = torch.from_numpy(qs).to(dev)
+                    dist.broadcast(t, src=0)
+                    qs = t.cpu().numpy()
+                sec, r = timed_e2e(lambda: search(qs, k), 3)
+                if rank == 0:
+                    assert int(r[0][0, 0]) == 0 and float(r[1][0, 0]) == 0.0
+                sweeps["batch_sweep_k10"].append({"queries": nq, "ms_per_batch": sec * 1e3, "queries_per_s": nq / sec,
+                                                  "path": "tcgen05 filter + exact rescoring (fp32 store: bf16 shadow)"})
+
+        out = {"exchange": exchange, "sweeps": sweeps, "n": n, "steps": n_steps, "ms_dev": ms_dev, "launches": launches, "scan_ms": scan_ms,
                "n_scans": n_scans, "e2e_s": e2e_s, "scan_bytes": store.scan_bytes(),
                "t_wall": (t_wall0, t_wall1), "parity": "skipped (--no-parity)"}
 
@@ -450,7 +488,7 @@ def run_b200(args):
     main = measure(args.rows_per_gpu, steps, not args.no_parity)
     extra = None
     if not args.no_extra and args.rows_per_gpu != ROWS_EXTRA:
-        extra = measure(ROWS_EXTRA, max(steps, 200), not args.no_parity)
+        extra = measure(ROWS_EXTRA, max(steps, 200), not args.no_parity, sweep=not args.no_sweeps)
     sampler.stop()
     if comm is not None:
         comm.close()
@@ -508,6 +546,8 @@ def run_b200(args):
     if extra is not None:
         se = summarize(extra)
         line["extra_1m"] = {"config": workload_config(world, ROWS_EXTRA, k), "steps": extra["steps"], **se}
+        if extra.get("sweeps"):
+            line["extra_1m"]["sweeps"] = extra["sweeps"]
     if world == 1 and not args.no_cpu_baseline:
         try:
             from oracle import c_oracle as co

@@ -147,6 +147,12 @@ impl GpuVectorstore {
         check(unsafe { ffi::bsr_store_set_metric(self.handle, if dot { ffi::BSR_DOT } else { ffi::BSR_COSINE }) })
     }
 
+    /// Ablation switch / test hook of this handle (`bsr_store_set_option`, include/bsr.h).
+    pub fn set_option(&mut self, name: &str, value: i64) -> Result<(), BsrError> {
+        let c = std::ffi::CString::new(name).map_err(|_| BsrError { status: -1, message: "bad option name".into() })?;
+        check(unsafe { ffi::bsr_store_set_option(self.handle, c.as_ptr(), value) })
+    }
+
     pub fn reset(&mut self) -> Result<(), BsrError> {
         check(unsafe { ffi::bsr_store_reset(self.handle) })
     }
@@ -269,6 +275,13 @@ impl DeviceWorld {
         let mut handle = std::ptr::null_mut();
         check(unsafe { ffi::bsr_comm_create(id.as_ptr(), size, rank, device, &mut handle) })?;
         Ok(Self { handle, rank, size })
+    }
+    /// True when single-query searches with top_k <= 128 exchange their candidates through NVLink peer
+    /// stores fused into the scan kernel (one kernel per rank and query) instead of ncclAllGather.
+    pub fn uses_mailbox(&self) -> Result<bool, BsrError> {
+        let mut yes: c_int = 0;
+        check(unsafe { ffi::bsr_comm_uses_mailbox(self.handle, &mut yes) })?;
+        Ok(yes != 0)
     }
 }
 
