@@ -82,6 +82,7 @@ struct Knobs {
     int no_param_query = 0;  // BSR_NO_PARAM_QUERY: bsr_search always copies the query and waits on the stream
     int no_pdl = 0;          // BSR_NO_PDL: plain stream-ordered launches for back-to-back scans
     int no_mailbox = 0;      // BSR_NO_MAILBOX: cross-rank exchange through ncclAllGather only
+    int no_small = 0;        // BSR_NO_SMALL: stores of one panel per warp through the streaming kernel too
 };
 static const Knobs& knobs() {
     static const Knobs k = [] {
@@ -108,6 +109,7 @@ static const Knobs& knobs() {
         v.no_param_query = getenv("BSR_NO_PARAM_QUERY") != nullptr;
         v.no_pdl = getenv("BSR_NO_PDL") != nullptr;
         v.no_mailbox = getenv("BSR_NO_MAILBOX") != nullptr;
+        v.no_small = getenv("BSR_NO_SMALL") != nullptr;
         return v;
     }();
     return k;
@@ -176,6 +178,8 @@ struct bsr_store {
     bool busy = false;
     cudaEvent_t ev_scan0 = nullptr, ev_scan1 = nullptr;
     bool scan_timed = false;
+    bool scan_time_in_ll = false;  // the last scan published its own duration (FinalOut::t_start)
+    u32 last_scan_ns = 0;
 
     // optional per-launch timing of the scan kernel (bsr_store_set_profiling)
     bool profiling = false;
@@ -725,6 +729,62 @@ static int launch_scan_bulk_t(bsr_store* s, const ScanArgs& a, unsigned grid, u3
     return BSR_OK;
 }
 
+// Stores of at most one panel per warp, fp32, one host query in the parameter block: scan_small_kernel.
+// Ring depth: the whole panel per live warp when that fits, else as deep as fits.
+static bool small_scan_applies(const bsr_store* s, u32 n_panels, unsigned grid, u32 K, u32* stages, u32* live) {
+    if (s->kn.no_small || is_bf16(s) || !s->param_query || s->dim > kParamQueryMax) return false;
+    if (s->dq % kChunkQuads != 0 || n_panels > grid * (u32)kBulkWarps) return false;
+    const u32 cpp = s->dq / kChunkQuads;
+    const u32 lv = (n_panels + grid - 1) / grid;
+    u32 st = cpp;
+    while (st >= 2 && bulk_smem_bytes(s, K, st, 1, lv) + 1024 > s->smem_optin) st--;
+    if (st < 2 || lv * st > (u32)kBulkWarps * 32u) return false;
+    *stages = st;
+    *live = lv;
+    return true;
+}
+template <bool WHOLE, int NB>
+static int launch_scan_small_t(bsr_store* s, const ScanArgs& a, unsigned grid, u32 stages, u32 live, cudaStream_t st) {
+    static thread_local bool configured[64] = {false};
+    if (!configured[s->device & 63]) {
+        cudaFuncAttributes fa;
+        CU(cudaFuncGetAttributes(&fa, scan_small_kernel<kBulkWarps, WHOLE, NB>));
+        CU(cudaFuncSetAttribute(scan_small_kernel<kBulkWarps, WHOLE, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(s->smem_optin - fa.sharedSizeBytes)));
+        configured[s->device & 63] = true;
+    }
+    BulkScanArgs ba;
+    ba.s = a;
+    ba.stages = stages;
+    ba.active_warps = live;
+    ba.interleave = 1u;
+    ba.panel_ticket = nullptr;
+    // |b|: by the CTAs' idle warp when there is one (every CTA has at most `live` panels), else here
+    const bool mag_on_device = live < (u32)kBulkWarps;
+    ba.query_in_params = mag_on_device ? 2 : 1;
+    memset(ba.qparam, 0, sizeof(ba.qparam));
+    memcpy(ba.qparam, s->param_query, (size_t)s->dim * sizeof(float));
+    ba.qparam_mag = mag_on_device ? 0.0f : host_query_magnitude(s->param_query, s->dim);
+    scan_small_kernel<kBulkWarps, WHOLE, NB>
+        <<<grid, kBulkWarps * 32, bulk_smem_bytes(s, a.k_pad, stages, 1, live), st>>>(ba);
+    s->launches++;
+    CU(cudaGetLastError());
+    return BSR_OK;
+}
+template <bool WHOLE>
+static int launch_scan_small_w(bsr_store* s, const ScanArgs& a, unsigned grid, u32 stages, u32 live, cudaStream_t st) {
+    // register epilogue: k_pad <= 128 with the final stage fused into the launch, at most 20 CTA lists per warp
+    const bool regs = a.fuse_final && a.k_pad <= 128 && grid <= 20u * kBulkWarps;
+    if (regs && a.k_pad == 32) return launch_scan_small_t<WHOLE, 1>(s, a, grid, stages, live, st);
+    if (regs && a.k_pad == 64) return launch_scan_small_t<WHOLE, 2>(s, a, grid, stages, live, st);
+    if (regs && a.k_pad == 128) return launch_scan_small_t<WHOLE, 4>(s, a, grid, stages, live, st);
+    return launch_scan_small_t<WHOLE, 0>(s, a, grid, stages, live, st);
+}
+static int launch_scan_small(bsr_store* s, const ScanArgs& a, unsigned grid, u32 stages, u32 live, cudaStream_t st) {
+    return stages == s->dq / kChunkQuads ? launch_scan_small_w<true>(s, a, grid, stages, live, st)
+                                         : launch_scan_small_w<false>(s, a, grid, stages, live, st);
+}
+
 template <int QB>
 static int launch_scan_bulk(bsr_store* s, const ScanArgs& a, unsigned grid, u32 stages, u32 active_warps,
                             cudaStream_t st, u32* panel_ticket) {
@@ -1069,7 +1129,9 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
     TRY(ensure(s->merge_b, inter));
     const u32 max_qb = bulk ? bulk_max_qb(s, K) : 1;
 
-    CU(cudaEventRecord(s->ev_scan0, st));
+    // one-launch searches time themselves (FinalOut::t_start): no events in their stream
+    const bool ll_timed = fuse && nq == 1 && s->host_ll != nullptr;
+    if (!ll_timed) CU(cudaEventRecord(s->ev_scan0, st));
     for (u32 q = 0; q < nq;) {
         // queries are scanned in groups that share one pass over the store
         u32 qb = max_qb;
@@ -1096,6 +1158,7 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
         a.fin.host_ll = (fuse && nq == 1) ? s->host_ll : nullptr;
         a.fin.ll_k = s->ll_k;
         a.fin.ll_seq = s->ll_seq;
+        a.fin.t_start = a.fin.host_ll ? (unsigned long long*)((char*)s->d_counter.p + 128) : nullptr;
         a.fin.mb = Mailbox{};
         if (s->mailbox && fuse && nq == 1) a.fin.mb = *s->mailbox;
         a.dbg = a.fin.dbg = nullptr;
@@ -1114,7 +1177,10 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
         }
 #endif
         TRY(prof_begin(s, st));
-        if (bulk) {
+        u32 small_stages = 0, small_live = 0;
+        if (bulk && qb == 1 && small_scan_applies(s, n_panels, grid, K, &small_stages, &small_live)) {
+            TRY(launch_scan_small(s, a, grid, small_stages, small_live, st));
+        } else if (bulk) {
             if (qb == 1 && wide) {
                 const u32 stages = bulk_stages(s, K, 1, active_warps, small_store, 16);
                 u32* const tk = (!small_store && !s->kn.no_tickets && stages <= cpp) ? ticket : nullptr;
@@ -1149,6 +1215,7 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
                                           "last: lists folded", "last: done"};
             fprintf(stderr, "scan timeline (ns since cta0 start), grid %u:", grid);
             for (int i = 0; i < 11; i++) fprintf(stderr, " [%s %lld]", names[i], h_dbg[i] ? (long long)(h_dbg[i] - h_dbg[0]) : -1LL);
+            if (h_dbg[14]) fprintf(stderr, " [cta0 requests issued %lld] [cta0 query staged %lld]", (long long)(h_dbg[14] - h_dbg[0]), (long long)(h_dbg[15] - h_dbg[0]));
             if (h_dbg[13] > h_dbg[12] && h_dbg[4] > h_dbg[0])
                 fprintf(stderr, " [SM clock %.0f MHz over the panel loop]", (double)(h_dbg[13] - h_dbg[12]) * 1e3 / (double)(h_dbg[4] - h_dbg[0]));
             fprintf(stderr, "\n  cta0 warp0 chunks, SM cycles since the first wait (wait->ready):");
@@ -1159,8 +1226,9 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
 #endif
         q += qb;
     }
-    CU(cudaEventRecord(s->ev_scan1, st));
+    if (!ll_timed) CU(cudaEventRecord(s->ev_scan1, st));
     s->scan_timed = true;
+    s->scan_time_in_ll = ll_timed;
     if (fuse) return BSR_OK;
     TRY(merge_tree(s, (const u64*)s->cta_keys.p, grid, nq, K, k, K, (size_t)grid * K, d_cand, st));
     if (d_idx) {
@@ -1236,7 +1304,7 @@ extern "C" int bsr_unpack_device(bsr_store* s, const uint64_t* d_cand, uint32_t 
 // own.  Every ~1 000 polls the stream is asked as well, so a failed launch or a faulting kernel
 // surfaces as an error instead of a hang.
 static int wait_host_ll(bsr_store* s, const volatile u64* ll, u32 seq, u32 k, uint64_t* out_idx, float* out_dist,
-                        uint32_t* out_count) {
+                        uint32_t* out_count, bool timed) {
     auto wait_word = [&](u32 i, u32* value) -> int {
         for (u32 spins = 0;; spins++) {
             const u64 w = ll[i];
@@ -1271,6 +1339,7 @@ static int wait_host_ll(bsr_store* s, const volatile u64* ll, u32 seq, u32 k, ui
         memcpy(&out_dist[j], &v, sizeof(float));
     }
     if (out_count) *out_count = count;
+    if (timed) TRY(wait_word(2 * k + 1, &s->last_scan_ns));
     return BSR_OK;
 }
 
@@ -1294,7 +1363,7 @@ extern "C" int bsr_search(bsr_store* s, const float* queries, uint32_t nq, uint3
     const size_t rbytes = ibytes + dbytes + cbytes;
     const size_t off_r = (qbytes + 15) & ~(size_t)15;
     const size_t off_ll = (off_r + rbytes + 63) & ~(size_t)63;  // one-launch searches: (2k + 1) self-validating words
-    TRY(ensure_pinned(s, off_ll + (2 * (size_t)k + 1) * sizeof(u64)));
+    TRY(ensure_pinned(s, off_ll + (2 * (size_t)k + 2) * sizeof(u64)));
     TRY(ensure(s->d_queries, qbytes));
     TRY(ensure(s->d_cand, (size_t)nq * K * sizeof(u64)));
     TRY(ensure(s->d_result, rbytes));
@@ -1322,7 +1391,7 @@ extern "C" int bsr_search(bsr_store* s, const float* queries, uint32_t nq, uint3
         s->host_ll = (u64*)ll;
         s->ll_k = k;
         next_ll_seq(s);
-        for (u32 i = 0; i < 2 * k + 1; i++) ll[i] = 0;  // whatever an earlier call left in these words of the shared block
+        for (u32 i = 0; i < 2 * k + 2; i++) ll[i] = 0;  // whatever an earlier call left in these words of the shared block
     } else {
         memcpy(h, queries, qbytes);
     }
@@ -1371,7 +1440,7 @@ extern "C" int bsr_search(bsr_store* s, const float* queries, uint32_t nq, uint3
     s->tensor_min_batch = saved_min_batch;
     TRY(rc);
     if (one_launch) {
-        TRY(wait_host_ll(s, ll, s->ll_seq, k, out_idx, out_dist, out_count));
+        TRY(wait_host_ll(s, ll, s->ll_seq, k, out_idx, out_dist, out_count, s->scan_time_in_ll));
         // the kernel may still be retiring; the next call on this handle is stream-ordered behind it
         mark_idle(s);
         return BSR_OK;
@@ -1757,7 +1826,7 @@ extern "C" int bsr_search_parallel(bsr_store* s, bsr_comm* c, const float* queri
     // the two buffers the exchange itself needs; without them this rank cannot take part at all
     TRY(ensure(s->d_cand, cand_bytes));
     TRY(ensure(s->d_gather, cand_bytes * c->n_ranks + cand_bytes));
-    TRY(ensure_pinned(s, off_flag + (2 * (size_t)k + 1) * sizeof(u64)));
+    TRY(ensure_pinned(s, off_flag + (2 * (size_t)k + 2) * sizeof(u64)));
     TRY(order_after_previous(s, s->stream));
     char* h = (char*)s->h_pinned;
 
@@ -1769,7 +1838,7 @@ extern "C" int bsr_search_parallel(bsr_store* s, bsr_comm* c, const float* queri
         volatile u64* ll = (volatile u64*)(h + off_flag);
         const u32 ll_k = root ? k : 0;  // the other ranks only signal completion (the count word)
         const u32 ll_seq = next_ll_seq(s);
-        for (u32 i = 0; i < 2 * ll_k + 1; i++) ll[i] = 0;
+        for (u32 i = 0; i < 2 * ll_k + 2; i++) ll[i] = 0;
         int local_rc = BSR_OK;
         if (s->n_rows != 0) {
             const bool in_params = s->dim <= kParamQueryMax && !s->kn.no_param_query;
@@ -1795,10 +1864,11 @@ extern "C" int bsr_search_parallel(bsr_store* s, bsr_comm* c, const float* queri
         }
         char local_err[sizeof g_err];
         if (local_rc != BSR_OK) memcpy(local_err, g_err, sizeof g_err);
-        if (s->n_rows == 0 || local_rc != BSR_OK)
+        const bool scanned = s->n_rows != 0 && local_rc == BSR_OK;
+        if (!scanned)
             TRY(launch_mailbox_only(s, mb, k, (u64*)s->d_cand.p, (u64*)ll, ll_k, ll_seq, s->stream));
         u32 cnt = 0;
-        TRY(wait_host_ll(s, ll, ll_seq, ll_k, out_idx, out_dist, &cnt));
+        TRY(wait_host_ll(s, ll, ll_seq, ll_k, out_idx, out_dist, &cnt, scanned && s->scan_time_in_ll));
         mark_idle(s);
         if (local_rc != BSR_OK) {
             memcpy(g_err, local_err, sizeof g_err);
@@ -1945,6 +2015,10 @@ extern "C" int bsr_store_launch_count(const bsr_store* s, uint64_t* n) {
 extern "C" int bsr_store_last_scan_ms(bsr_store* s, float* ms) {
     CHECK(s && ms, BSR_ERR_INVALID, "bsr_store_last_scan_ms: null argument");
     CHECK(s->scan_timed, BSR_ERR_INVALID, "bsr_store_last_scan_ms: no scan has run on this store");
+    if (s->scan_time_in_ll) {  // a one-launch search: measured by the launch itself (FinalOut::t_start)
+        *ms = (float)s->last_scan_ns * 1e-6f;
+        return BSR_OK;
+    }
     DeviceGuard g(s->device);
     CU(cudaEventSynchronize(s->ev_scan1));
     CU(cudaEventElapsedTime(ms, s->ev_scan0, s->ev_scan1));
@@ -1995,7 +2069,7 @@ extern "C" int bsr_store_set_option(bsr_store* s, const char* name, int64_t valu
         {"tc_stats", &s->kn.tc_stats},         {"no_pdl", &s->kn.no_pdl},
         {"wide", &s->kn.wide},                 {"no_tickets", &s->kn.no_tickets},
         {"no_param_query", &s->kn.no_param_query}, {"no_f32_tensor", &s->kn.no_f32_tensor},
-        {"no_mailbox", &s->kn.no_mailbox},
+        {"no_mailbox", &s->kn.no_mailbox},     {"no_small", &s->kn.no_small},
     };
     for (auto& t : table)
         if (strcmp(t.name, name) == 0) {

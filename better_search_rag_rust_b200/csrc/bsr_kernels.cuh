@@ -70,9 +70,16 @@ __device__ __forceinline__ bool differs4(const float4& a, const float4& q) {
 // Bitwise-equal quads never "differ" (a - a is 0, or NaN for NaN / inf, and neither is > 1e-10): the
 // common case on the one row that IS the query (the reference's self-query) costs three integer ops
 // per quad instead of four subtract-compare pairs.
+// (a ^ b) | c as ONE lop3.  Written in PTX on purpose: from C the compiler rewrites "an OR of XORs is
+// zero" into a chain of predicated integer compares (ISETP.EQ.AND P0, .., P0), one dependent
+// predicate round trip per column -- ~13 cycles each on the lone lane every other lane waits for.
+__device__ __forceinline__ u32 xor_or(float a, float b, u32 c) {
+    u32 d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xBE;" : "=r"(d) : "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(c));
+    return d;
+}
 __device__ __forceinline__ bool differs4_fast(const float4& a, const float4& q) {
-    const u32 x = (__float_as_uint(a.x) ^ __float_as_uint(q.x)) | (__float_as_uint(a.y) ^ __float_as_uint(q.y)) |
-                  (__float_as_uint(a.z) ^ __float_as_uint(q.z)) | (__float_as_uint(a.w) ^ __float_as_uint(q.w));
+    const u32 x = xor_or(a.x, q.x, xor_or(a.y, q.y, 0u)) | xor_or(a.z, q.z, xor_or(a.w, q.w, 0u));
     return x != 0u && differs4(a, q);
 }
 
@@ -568,13 +575,24 @@ struct FinalOut {
     // posted PCIe write to be acknowledged), no waiting for the grid to retire and the stream to signal.
     // ll_k == 0 (a non-root rank of a multi-rank search): only the count word, as a completion signal.
     // nullptr: results go to idx / dist / count.
+    //   host_ll[2 ll_k + 1]       (t_start != nullptr) nanoseconds from the first CTA's first instruction to
+    //                             this word's store: what bsr_store_last_scan_ms reports for such a launch.
+    //                             Two timing events around the launch would cost a small store's search
+    //                             ~1.1 us of its ~20 (measured); the first CTA leaves %globaltimer in
+    //                             *t_start (device memory), the last CTA reads it back after the ticket.
     u64* host_ll;
     u32 ll_k;
     u32 ll_seq;
+    unsigned long long* t_start;
     Mailbox mb;         // cross-rank exchange fused into the last CTA (k <= 128, one query); all-null: none
     unsigned long long* dbg;  // debug stamps (see ScanArgs::dbg)
 };
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void ll_store(u64* p, u32 seq, u32 value) {
     *reinterpret_cast<volatile u64*>(p) = ((u64)seq << 32) | (u64)value;
 }
@@ -586,15 +604,18 @@ __device__ __forceinline__ void ll_publish_entry(const FinalOut& fo, u32 j, u64 
     ll_store(fo.host_ll + fo.ll_k + j, fo.ll_seq, ok ? bits_from_ordered((u32)(v >> 32)) : 0u);
 }
 __device__ __forceinline__ void ll_publish_count(const FinalOut& fo, u32 count) {
+    if (fo.t_start) {  // the launch's own duration (see FinalOut::t_start), ns, saturating
+        const unsigned long long ns = globaltimer_ns() - *reinterpret_cast<const volatile unsigned long long*>(fo.t_start);
+        ll_store(fo.host_ll + 2 * fo.ll_k + 1, fo.ll_seq, ns < 0xFFFFFFFFull ? (u32)ns : 0xFFFFFFFFu);
+    }
     ll_store(fo.host_ll + 2 * fo.ll_k, fo.ll_seq, count);
+}
+// first thing a scan kernel does (see FinalOut::t_start)
+__device__ __forceinline__ void ll_stamp_start(const FinalOut& fo) {
+    if (fo.host_ll && fo.t_start && blockIdx.x == 0 && threadIdx.x == 0) *fo.t_start = globaltimer_ns();
 }
 
 #ifdef BSR_TC_TIMELINE
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 // CTA 0 thread 0 stamps slots 0-7; the last CTA to finish stamps 8-11 (see scan_epilogue)
 #define BSR_STAMP(dbg, cond, slot) do { if ((dbg) && (cond)) (dbg)[slot] = globaltimer_ns(); } while (0)
 #else
@@ -824,6 +845,7 @@ struct ScanArgs {
 template <int U>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_f32_kernel(const ScanArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    ll_stamp_start(a.fin);
     float4* sq = reinterpret_cast<float4*>(smem_raw);
     u64* lists = reinterpret_cast<u64*>(smem_raw + (size_t)a.dq * sizeof(float4));
 
@@ -949,6 +971,17 @@ __device__ __forceinline__ bool mbar_try_wait(u32 bar, u32 parity) {
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ u32 mbar_try_wait_u32(u32 bar, u32 parity) {  // 1: the phase has completed
+    u32 ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
 __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
@@ -990,12 +1023,13 @@ struct BulkScanArgs {
     // Zero before the launch; the last CTA to finish resets it (needs ScanArgs::fin.done_counter).
     u32* panel_ticket;
     // Single host query (bsr_search, dim <= kParamQueryMax): the query travels in the kernel's
-    // parameter block (constant bank) instead of a separate host-to-device copy.
+    // parameter block (constant bank) instead of a separate host-to-device copy.  2 (scan_small_kernel
+    // only): ... and qparam_mag is not set, a warp without a panel computes |b|.
     u32 query_in_params;
     // ... and its magnitude |b| (src/metrics.rs:155, the same sequential fold, done once on the host)
     // so that no warp runs the second 768-step chain next to its first panel's dot products.
     float qparam_mag;
-    float qparam[768];
+    alignas(16) float qparam[768];  // zero-padded by the host (read as float4 by scan_small_kernel)
 };
 constexpr u32 kParamQueryMax = 768;
 
@@ -1013,6 +1047,7 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const __grid_
     const ScanArgs& a = ba.s;
     constexpr int CH = kChunkQuads;                    // fp32: column-quads per 4 KiB chunk
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    ll_stamp_start(a.fin);
     BSR_STAMP(a.dbg, blockIdx.x == 0 && threadIdx.x == 0, 0);
 #ifdef BSR_TC_TIMELINE
     if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[12] = (unsigned long long)clock64();
@@ -1197,14 +1232,28 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const __grid_
             }
             if (maybe_mask) {
                 // rare: my row has matched a query on every column so far -- compare this block too
-                // (out of the hot loop: the stage is still in shared memory)
-                for (u32 cc = 0; cc < 8; cc++) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(rp + ((cc ^ sw) << 4));
+                // (out of the hot loop: the stage is still in shared memory).  Bitwise-equal columns never
+                // differ: four lop3 chains over the block first (see xor_or), the subtract-compare pass
+                // only for a query some bit of which differs
 #pragma unroll
-                    for (int b = 0; b < QB; b++)
-                        if (((maybe_mask >> b) & 1u) &&
-                            differs8_bf16(v, sq[(q0i + 2 * cc) * QB + b], sq[(q0i + 2 * cc + 1) * QB + b]))
+                for (int b = 0; b < QB; b++) {
+                    if (!((maybe_mask >> b) & 1u)) continue;
+                    u32 x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+#pragma unroll
+                    for (u32 cc = 0; cc < 8; cc++) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(rp + ((cc ^ sw) << 4));
+                        const float4 qa = sq[(q0i + 2 * cc) * QB + b], qb2 = sq[(q0i + 2 * cc + 1) * QB + b];
+                        x0 = xor_or(bf16_lo(v.x), qa.x, xor_or(bf16_hi(v.x), qa.y, x0));
+                        x1 = xor_or(bf16_lo(v.y), qa.z, xor_or(bf16_hi(v.y), qa.w, x1));
+                        x2 = xor_or(bf16_lo(v.z), qb2.x, xor_or(bf16_hi(v.z), qb2.y, x2));
+                        x3 = xor_or(bf16_lo(v.w), qb2.z, xor_or(bf16_hi(v.w), qb2.w, x3));
+                    }
+                    if (!((x0 | x1) | (x2 | x3))) continue;
+                    for (u32 cc = 0; cc < 8; cc++) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(rp + ((cc ^ sw) << 4));
+                        if (differs8_bf16(v, sq[(q0i + 2 * cc) * QB + b], sq[(q0i + 2 * cc + 1) * QB + b]))
                             maybe_mask &= ~(1u << b);
+                    }
                 }
             }
         } else {
@@ -1265,14 +1314,16 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const __grid_
                         if ((maybe_mask >> b) & 1u) {
                             // bitwise-equal columns never differ (differs4_fast): one OR-reduction over the
                             // chunk, branch-free; the subtract-compare pass only if some bit differs
-                            u32 x = 0;
+                            u32 x0 = 0, x1 = 0, x2 = 0, x3 = 0;  // four independent lop3 chains (see xor_or)
 #pragma unroll
                             for (int u = 0; u < CH; u++) {
                                 const float4 q = sq[(j0 + u) * QB + b];
-                                x |= (__float_as_uint(v[u].x) ^ __float_as_uint(q.x)) | (__float_as_uint(v[u].y) ^ __float_as_uint(q.y)) |
-                                     (__float_as_uint(v[u].z) ^ __float_as_uint(q.z)) | (__float_as_uint(v[u].w) ^ __float_as_uint(q.w));
+                                x0 = xor_or(v[u].x, q.x, x0);
+                                x1 = xor_or(v[u].y, q.y, x1);
+                                x2 = xor_or(v[u].z, q.z, x2);
+                                x3 = xor_or(v[u].w, q.w, x3);
                             }
-                            if (x) {
+                            if ((x0 | x1) | (x2 | x3)) {
                                 bool d = false;
 #pragma unroll
                                 for (int u = 0; u < CH; u++) d |= differs4(v[u], sq[(j0 + u) * QB + b]);
@@ -1367,6 +1418,438 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const __grid_
     const u32 cta_panels = blockIdx.x < a.n_panels ? (a.n_panels - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     scan_epilogue<W, QB>(lists, K, a.k, a.cta_keys, a.fin, a.fuse_final != 0, ba.panel_ticket,
                          min(cta_panels, (u32)W));
+}
+
+// One warp's 32 keys (one per lane) -> slot[0..32) ascending, through the slots themselves: every lane
+// reads all 32 keys back (broadcast reads) and counts the ones ahead of its own.  ~200 cycles of
+// independent loads and compares; a bitonic sort of the same keys is 15 dependent shuffle stages (~800).
+// Equal keys (only the empty key repeats: rows past the end of the store) are ordered by lane.
+__device__ __forceinline__ void warp_rank_sort32(u64* slot, u64 key, int lane) {
+    slot[lane] = key;
+    __syncwarp();
+    u32 rank = 0;
+    const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(slot);  // 16-byte aligned (host layout)
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const ulonglong2 p = s2[i];
+        rank += (p.x < key || (p.x == key && 2 * i < lane)) ? 1u : 0u;
+        rank += (p.y < key || (p.y == key && 2 * i + 1 < lane)) ? 1u : 0u;
+    }
+    __syncwarp();
+    slot[rank] = key;
+}
+
+// ------------------------------------------------------------------------------------------
+// Register-resident epilogue of scan_small_kernel (top_k <= 128: NB = k_pad / 32 blocks of 32 keys per
+// lane).  A small store's epilogue is a chain of list merges, each ~6 shuffle stages of ~55 cycles on a
+// warp that has nothing else to issue -- so the merges are arranged as TREES whose independent nodes the
+// compiler interleaves (straight-line code, no data-dependent skips), instead of one running list that
+// takes every other list in turn: 73 CTA lists are 4 + 3 merge latencies deep instead of 10 + 7.
+// ------------------------------------------------------------------------------------------
+// a, b: ascending lists of NB*32 keys (block j = keys 32j .. 32j+31, lane i holds key 32j+i).
+// Leaves the NB*32 smallest of the two in a, ascending.
+template <int NB>
+__device__ __forceinline__ void merge_keep(u64 (&a)[NB], const u64 (&b)[NB], int lane) {
+    // a_i against b_(K-1-i): the K minima are the K smallest of the 2K and form a bitonic sequence
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        const u64 r = __shfl_sync(0xFFFFFFFFu, b[NB - 1 - j], 31 - lane);
+        a[j] = a[j] < r ? a[j] : r;
+    }
+    // bitonic merge: distances >= 32 are between registers, 16 .. 1 between lanes
+#pragma unroll
+    for (int dj = NB / 2; dj >= 1; dj >>= 1) {
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+            if ((j & dj) == 0) {
+                const u64 x = a[j], y = a[j + dj];
+                a[j] = x < y ? x : y;
+                a[j + dj] = x < y ? y : x;
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+            const u64 p = __shfl_xor_sync(0xFFFFFFFFu, a[j], d);
+            const bool keep_min = (lane & d) == 0;
+            a[j] = (keep_min == (a[j] < p)) ? a[j] : p;
+        }
+    }
+}
+// N lists -> t[0], pairwise: every level's merges are independent of one another
+template <int NB, int N>
+__device__ __forceinline__ void merge_tree_regs(u64 (&t)[N][NB], int lane) {
+#pragma unroll
+    for (int s = 1; s < N; s <<= 1) {
+#pragma unroll
+        for (int i = 0; i + s < N; i += 2 * s) merge_keep<NB>(t[i], t[i + s], lane);
+    }
+}
+// this warp's share (lists warp, warp + W, ...) of the n_lists CTA lists in global memory -> best
+template <int NB, int W, int N>
+__device__ __forceinline__ void fold_cta_lists_tree(const u64* src, u32 n_lists, u64 (&best)[NB], int warp, int lane) {
+    constexpr u32 K = NB * 32;
+    u64 t[N][NB];
+#pragma unroll
+    for (int i = 0; i < N; i++) {  // every load first: one L2 round trip
+        const u32 l = (u32)warp + (u32)i * W;
+#pragma unroll
+        for (int j = 0; j < NB; j++) t[i][j] = l < n_lists ? ldcg_u64(src + (size_t)l * K + j * 32 + lane) : kKeyMax;
+    }
+    merge_tree_regs<NB, N>(t, lane);
+#pragma unroll
+    for (int j = 0; j < NB; j++) best[j] = t[0][j];
+}
+
+// lists: shared memory, on entry [W][32] -- warp w's 32 keys, ascending (warps >= live: unused) -- and W*K
+// keys of room.  Same contract as scan_epilogue<W, 1> for K = NB*32 <= 128 with the final stage fused.
+template <int W, int NB>
+__device__ __forceinline__ void small_epilogue(u64* lists, u32 live, u32 k, u64* cta_keys, const FinalOut& fo,
+                                               bool fuse_final) {
+    constexpr u32 K = NB * 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ u32 s_is_last;
+    if (warp == 0) {
+        // the CTA's best K: this CTA's per-warp lists (one block each), padded with empty blocks
+        u64 t[W][NB];
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            t[w][0] = (u32)w < live ? lists[w * 32 + lane] : kKeyMax;
+#pragma unroll
+            for (int j = 1; j < NB; j++) t[w][j] = kKeyMax;
+        }
+        if (live > 1) merge_tree_regs<NB, W>(t, lane);
+#pragma unroll
+        for (int j = 0; j < NB; j++) cta_keys[(size_t)blockIdx.x * K + j * 32 + lane] = t[0][j];
+        if (fuse_final) {
+            // release: the stores above (ordered before lane 0's atomic by the warp barrier) are visible to
+            // whoever reads the counter's final value; acquire: the last CTA sees every other CTA's list
+            __syncwarp();
+            if (lane == 0) {
+                u32 ticket;
+                asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(fo.done_counter) : "memory");
+                s_is_last = (ticket == gridDim.x - 1) ? 1u : 0u;
+            }
+        }
+    }
+    BSR_STAMP(fo.dbg, blockIdx.x == 0 && tid == 0, 6);
+    if (!fuse_final) return;
+    __syncthreads();
+    BSR_STAMP(fo.dbg, blockIdx.x == 0 && tid == 0, 7);
+    if (!s_is_last) return;
+    BSR_STAMP(fo.dbg, tid == 0, 8);
+    // last CTA: every warp folds its share of the CTA lists, the W partial results meet in shared memory
+    u64 best[NB];
+    if (NB <= 2) {
+        if (gridDim.x <= 10u * W) fold_cta_lists_tree<NB, W, 10>(cta_keys, gridDim.x, best, warp, lane);
+        else fold_cta_lists_tree<NB, W, 20>(cta_keys, gridDim.x, best, warp, lane);  // host: gridDim.x <= 20 W
+    } else {
+#pragma unroll
+        for (int j = 0; j < NB; j++) best[j] = kKeyMax;
+        fold_cta_lists<NB, W>(cta_keys, gridDim.x, best, warp, lane);  // too many registers for a tree: one by one
+    }
+#pragma unroll
+    for (int j = 0; j < NB; j++) lists[(size_t)warp * K + j * 32 + lane] = best[j];
+    __syncthreads();
+    BSR_STAMP(fo.dbg, tid == 0, 9);
+    if (warp == 0) {
+        u64 t[W][NB];
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+#pragma unroll
+            for (int j = 0; j < NB; j++) t[w][j] = lists[(size_t)w * K + j * 32 + lane];
+        }
+        merge_tree_regs<NB, W>(t, lane);
+        if (NB == 1) {
+            const u64 v = mailbox_exchange32(t[0][0], fo.mb, k, lane);  // multi-rank: send to root / fold the peers in
+            fo.keys[lane] = (u32)lane < k ? v : kKeyMax;  // slots past top_k are published empty
+            if (fo.idx) {
+                const bool ok = (u32)lane < k && v != kKeyMax;
+                if ((u32)lane < k) {
+                    fo.idx[lane] = ok ? (v & 0xFFFFFFFFull) : 0ull;
+                    fo.dist[lane] = ok ? __uint_as_float(bits_from_ordered((u32)(v >> 32))) : 0.0f;
+                }
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+                if (lane == 0) fo.count[0] = (u32)__popc(m);
+            }
+            if (fo.host_ll) {
+                ll_publish_entry(fo, (u32)lane, v);
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, (u32)lane < fo.ll_k && v != kKeyMax);
+                if (lane == 0) ll_publish_count(fo, (u32)__popc(m));
+            }
+            if (lane == 0) *fo.done_counter = 0;
+        } else {
+            // 32 < K <= 128: the final list goes on through shared memory (the cross-rank exchange is
+            // CTA-wide); it overwrites partial list 0, which only this warp has read
+#pragma unroll
+            for (int j = 0; j < NB; j++) lists[j * 32 + lane] = t[0][j];
+        }
+    }
+    if (NB == 1) {
+        BSR_STAMP(fo.dbg, tid == 0, 10);
+        return;
+    }
+    __syncthreads();
+    u64* ql = lists;
+    mailbox_exchange_cta(ql, K, k, fo.mb);  // multi-rank: send to root / fold the peers in
+    u32 valid = 0, v_ok = 0;
+    if ((u32)tid < K) {  // K <= 128 <= blockDim.x: one key per thread, warps 0-3 hold them all
+        const u64 v = ql[tid];
+        const bool ok = v != kKeyMax;
+        fo.keys[tid] = (u32)tid < k ? v : kKeyMax;  // slots past top_k are published empty
+        if (fo.idx && (u32)tid < k) {
+            fo.idx[tid] = ok ? (v & 0xFFFFFFFFull) : 0ull;
+            fo.dist[tid] = ok ? __uint_as_float(bits_from_ordered((u32)(v >> 32))) : 0.0f;
+            valid = ok ? 1u : 0u;
+        }
+        if (fo.host_ll) {
+            ll_publish_entry(fo, (u32)tid, v);
+            v_ok = ((u32)tid < fo.ll_k && ok) ? 1u : 0u;
+        }
+    }
+    __shared__ u32 s_cnt[2][4];
+    const u32 wsum = __reduce_add_sync(0xFFFFFFFFu, valid), lsum = __reduce_add_sync(0xFFFFFFFFu, v_ok);
+    if (warp < 4 && lane == 0) {
+        s_cnt[0][warp] = wsum;
+        s_cnt[1][warp] = lsum;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (fo.idx) fo.count[0] = s_cnt[0][0] + s_cnt[0][1] + s_cnt[0][2] + s_cnt[0][3];
+        if (fo.host_ll) ll_publish_count(fo, s_cnt[1][0] + s_cnt[1][1] + s_cnt[1][2] + s_cnt[1][3]);
+        *fo.done_counter = 0;
+    }
+    BSR_STAMP(fo.dbg, tid == 0, 10);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1s: the scan for stores of at most ONE panel per warp (n_panels <= W * gridDim.x: up to ~38 k
+//      fp32 rows), one host query in the parameter block.  Same arithmetic, same layout, same
+//      epilogue as scan_topk_bulk_kernel<1, false, W>; what differs is that nothing here is built to
+//      stream.  A small store is a latency chain -- launch, first bytes, the reference's 768
+//      dependent adds per row (src/metrics.rs:152-156), the last-CTA fold -- and a warp that has its
+//      scheduler to itself pays every stall of the streaming loop in full (~800 cycles per 4 KiB chunk
+//      measured, 128 of them the add chain).  So:
+//        * every request of the CTA's first ring fill is issued by a different thread, spread over all
+//          W warps (the streaming kernel's lane 0 needs ~2 us for a panel's 24 requests);
+//        * a warp knows its one panel: no cursor, no ticket, no panel loop;
+//        * chunk c+1 is waited for and read into registers BEFORE chunk c's chain runs, so the
+//          barrier's try_wait and the shared-memory latency sit under the adds;
+//        * WHOLE: the ring holds the whole panel -- no refills, no slot arithmetic;
+//        * the warp's 32 keys are sorted in registers (one panel: nothing to insert into), and for
+//          top_k <= 128 the whole epilogue stays in registers (small_epilogue).
+// ------------------------------------------------------------------------------------------
+template <int W, bool WHOLE, int NB>
+__global__ void __launch_bounds__(W * 32, 1) scan_small_kernel(const __grid_constant__ BulkScanArgs ba) {
+    const ScanArgs& a = ba.s;
+    constexpr int CH = kChunkQuads;
+    constexpr u32 kChunkF4 = kChunkBytes / 16;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ll_stamp_start(a.fin);
+    BSR_STAMP(a.dbg, blockIdx.x == 0 && threadIdx.x == 0, 0);
+#ifdef BSR_TC_TIMELINE
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[12] = (unsigned long long)clock64();
+    __shared__ u32 s_tl[48];
+    if (threadIdx.x < 48) s_tl[threadIdx.x] = 0;
+#endif
+    // NB: k_pad / 32 for k_pad <= 128 (register epilogue, final stage fused); 0: any k_pad, scan_epilogue
+    const u32 dq = a.dq, S = ba.stages, K = NB ? 32u * NB : a.k_pad, cpp = dq / CH;  // host: dq % CH == 0, S <= cpp
+    // [ring: active_warps*S*4KiB | query: dq*16 | lists: W*K*8 | mbarriers: W*S*8] (as the streaming kernel)
+    unsigned char* ring_all = smem_raw;
+    float4* sq = reinterpret_cast<float4*>(ring_all + (size_t)ba.active_warps * S * kChunkBytes);
+    u64* lists = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(sq) + (size_t)dq * 16);
+    u64* bars = lists + (size_t)W * K;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // this CTA's panels are blockIdx.x, blockIdx.x + gridDim.x, ...: warp w owns the w-th of them
+    const u32 live = min((a.n_panels - 1 - blockIdx.x) / gridDim.x + 1, (u32)W);
+    const u64 policy = make_evict_first_policy();
+
+    // First ring fill: request r = (slot, warp), slot-major so that every warp's chunk 0 is asked for
+    // first; thread (warp r % W, lane r / W) initialises the request's barrier, arms it and issues the copy
+    {
+        const u32 r = (u32)lane * W + (u32)warp;
+        if (r < live * S) {
+            const u32 slot = r / live, w = r - slot * live;
+            const u32 bar = smem_u32(bars + (size_t)w * S + slot);
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const u32 p = w * gridDim.x + blockIdx.x;
+            mbar_expect_tx(bar, kChunkBytes);
+            bulk_g2s(smem_u32(ring_all + ((size_t)w * S + slot) * kChunkBytes),
+                     a.panels + (size_t)p * dq * 32 + (size_t)slot * kChunkF4, kChunkBytes, bar, policy);
+        }
+    }
+    BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 14);
+    // the query, zero-padded to the padded column count (parameter block: the host guarantees it)
+    // (one 16-byte constant load per thread: per-lane addresses in the constant bank are served one by
+    // one, and four scalar loads per thread made this loop 1.3 us of a 20 us search)
+    for (u32 j = tid; j < dq; j += (W * 32)) sq[j] = reinterpret_cast<const float4*>(ba.qparam)[j];
+    BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 15);
+    const bool has = (u32)warp < live;
+    const u32 panel = (u32)warp * gridDim.x + blockIdx.x;
+    const u32 row = panel * kPanelRows + lane;
+    const bool valid = has && row < a.n_rows;
+    const float mag_a = valid ? __ldg(a.norms + row) : 0.0f;
+    // a warp's result is its panel's 32 keys, sorted: lists[warp][32] for the register epilogue, a K-slot
+    // list padded with empty slots for scan_epilogue
+    const size_t my_list = (size_t)warp * (NB ? 32u : K);
+    if (!NB) {
+        for (u32 j = 32 + lane; j < K; j += 32) lists[my_list + j] = kKeyMax;
+        if (!has) lists[my_list + lane] = kKeyMax;
+    }
+    BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 1);
+    __syncthreads();
+    BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 2);
+
+    __shared__ float s_mag_b;
+    float acc_out = 0.0f;
+    bool maybe_out = false;
+    if (!has && ba.query_in_params == 2 && warp == W - 1) {
+        // |b| (src/metrics.rs:155, the same sequential fold) by a warp that has no panel: the host would
+        // spend ~1.3 us on these 768 dependent adds before it could launch; here they run next to the scan
+        float qs = 0.0f;
+        for (u32 j = 0; j < dq; j++) qs = sq4_seq(qs, sq[j]);  // the zero padding adds +0.0: exact
+        if (lane == 0) s_mag_b = __fsqrt_rn(qs);
+    }
+    if (has) {
+        const float4* sp = reinterpret_cast<const float4*>(ring_all + (size_t)warp * S * kChunkBytes) + lane;
+        const u32 ring = smem_u32(ring_all + (size_t)warp * S * kChunkBytes);
+        const u32 bar0 = smem_u32(bars + (size_t)warp * S);
+        const float4* src = a.panels + (size_t)panel * dq * 32;
+        // (slot, phase parity) of chunks c, c+1 and c+2; past the last chunk they stay on it (its phase stays
+        // complete), which keeps the loop body free of end-of-panel branches
+        auto adv = [&](u32& sl, u32& pa) {
+            if (++sl == S) {  // WHOLE: S == cpp, never reached
+                sl = 0;
+                pa ^= 1u;
+            }
+        };
+        u32 c = 0, s0 = 0, p0 = 0, s1 = 0, p1 = 0;
+        if (cpp > 1) adv(s1, p1);
+        u32 s2 = s1, p2 = p1;
+        if (cpp > 2) adv(s2, p2);
+        bool maybe = false;  // every column of my row seen so far is within 1e-10 of the query's (src/metrics.rs:7-19)
+        float acc = 0.0f;
+        // One chunk into registers and straight into its 32 products (independent, each rounded as the
+        // reference's); lanes whose row has matched the query so far compare it while it is there.
+        auto fetch = [&](float4(&pr)[CH], const float4* vp, const float4* qp, bool first) {
+            float4 v[CH], q[CH];
+#pragma unroll
+            for (int u = 0; u < CH; u++) v[u] = vp[u * 32];
+#pragma unroll
+            for (int u = 0; u < CH; u++) q[u] = qp[u];
+#pragma unroll
+            for (int u = 0; u < CH; u++) {
+                pr[u].x = __fmul_rn(v[u].x, q[u].x);
+                pr[u].y = __fmul_rn(v[u].y, q[u].y);
+                pr[u].z = __fmul_rn(v[u].z, q[u].z);
+                pr[u].w = __fmul_rn(v[u].w, q[u].w);
+            }
+            if (first) maybe = !differs4(v[0], q[0]);
+            // WHOLE: the panel stays in shared memory -- flagged rows are verified once, after the loop
+            if (!WHOLE && maybe) {  // rare (normally one lane of one warp: the row that IS the query)
+                u32 x0 = 0, x1 = 0, x2 = 0, x3 = 0;  // bitwise-equal columns never differ: four lop3 chains
+#pragma unroll
+                for (int u = 0; u < CH; u++) {
+                    x0 = xor_or(v[u].x, q[u].x, x0);
+                    x1 = xor_or(v[u].y, q[u].y, x1);
+                    x2 = xor_or(v[u].z, q[u].z, x2);
+                    x3 = xor_or(v[u].w, q[u].w, x3);
+                }
+                if ((x0 | x1) | (x2 | x3)) {
+                    bool d = false;
+#pragma unroll
+                    for (int u = 0; u < CH; u++) d |= differs4(v[u], q[u]);
+                    if (d) maybe = false;
+                }
+            }
+        };
+        float4 pa[CH], pb[CH];
+        mbar_wait(bar0, 0);
+        BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 3);
+        fetch(pa, sp, sq, true);
+        // The barrier of chunk c+1 is polled one step early (non-blocking try_wait whose result is read a
+        // step later), so the poll's latency sits under a chain as well.
+        u32 ok = mbar_try_wait_u32(bar0 + s1 * 8, p1);
+        // Step c: chunk c+1 is fetched and multiplied while chunk c's products are added in column order --
+        // the adds are a pure register chain (no scoreboard in it), everything that waits on shared memory
+        // runs in its latency slots.  The chain is made to depend on the wait's result, a constant 1 the
+        // compiler cannot know: otherwise ptxas hoists the whole chain above the wait and the reads end up
+        // behind it, every latency exposed.
+        auto step = [&](float4(&pr)[CH], float4(&pn)[CH]) {
+#ifdef BSR_TC_TIMELINE
+            if (a.dbg && blockIdx.x == 0 && tid == 0 && c < 24) s_tl[2 * c] = s_tl[2 * c + 1] = (u32)clock64();
+#endif
+            while (!ok) ok = mbar_try_wait_u32(bar0 + s1 * 8, p1);
+            acc = __uint_as_float(__float_as_uint(acc) | (ok ^ 1u));
+            const u32 ok2 = mbar_try_wait_u32(bar0 + s2 * 8, p2);
+            fetch(pn, sp + (size_t)s1 * kChunkF4, sq + (size_t)min(c + 1, cpp - 1) * CH, false);
+#pragma unroll
+            for (int u = 0; u < CH; u++) {
+                acc = __fadd_rn(acc, pr[u].x);
+                acc = __fadd_rn(acc, pr[u].y);
+                acc = __fadd_rn(acc, pr[u].z);
+                acc = __fadd_rn(acc, pr[u].w);
+            }
+            if (!WHOLE) {
+                __syncwarp();  // chunk c's slot was read a step ago: hand it back
+                if (lane == 0 && c + S < cpp) {
+                    mbar_expect_tx(bar0 + s0 * 8, kChunkBytes);
+                    bulk_g2s(ring + s0 * kChunkBytes, src + (size_t)(c + S) * kChunkF4, kChunkBytes, bar0 + s0 * 8, policy);
+                }
+            }
+            c++;
+            s0 = s1;
+            p0 = p1;
+            s1 = s2;
+            p1 = p2;
+            if (c + 2 < cpp) adv(s2, p2);
+            ok = ok2;
+        };
+        while (c < cpp) {
+            step(pa, pb);
+            if (c < cpp) step(pb, pa);
+        }
+        BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 4);
+#ifdef BSR_TC_TIMELINE
+        if (a.dbg && blockIdx.x == 0 && tid == 0) {
+            a.dbg[13] = (unsigned long long)clock64();
+            for (int i = 0; i < 48; i++) a.dbg[16 + i] = s_tl[i];
+        }
+#endif
+        if (WHOLE) {
+            // identity (src/metrics.rs:7-19) of the rows whose first four columns matched: the whole warp
+            // checks one flagged row at a time against the query, 32 column-quads per step
+            unsigned m = __ballot_sync(0xFFFFFFFFu, maybe);
+            maybe = false;
+            while (m) {
+                const int r = __ffs(m) - 1;
+                m &= m - 1;
+                bool diff = false;
+                for (u32 j = lane; j < dq; j += 32) diff |= differs4_fast(sp[(size_t)j * 32 + r - lane], sq[j]);
+                if (!__any_sync(0xFFFFFFFFu, diff) && lane == r) maybe = true;
+            }
+        }
+        acc_out = acc;
+        maybe_out = maybe;
+    }
+    float mag_b = ba.qparam_mag;
+    if (ba.query_in_params == 2) {  // |b| from this CTA's idle warp (below)
+        __syncthreads();
+        mag_b = s_mag_b;
+    }
+    if (has) {
+        u64 key = kKeyMax;
+        if (valid) key = make_key(finish_distance(acc_out, mag_a, mag_b, maybe_out, a.metric), a.row_base + row);
+        warp_rank_sort32(lists + my_list, key, lane);
+    }
+    __syncthreads();
+    BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 5);
+    if constexpr (NB != 0) small_epilogue<W, NB>(lists, live, a.k, a.cta_keys, a.fin, a.fuse_final != 0);
+    else scan_epilogue<W, 1>(lists, K, a.k, a.cta_keys, a.fin, a.fuse_final != 0, nullptr, live);
 }
 
 #ifndef BSR_TEMPLATES_ONLY  // the plain (non-template) kernels are compiled once, in bsr_api.cu
