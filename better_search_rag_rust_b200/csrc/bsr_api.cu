@@ -631,6 +631,34 @@ static float host_query_magnitude(const float* q, u32 dim) {
     return sqrtf(acc);
 }
 
+#ifdef BSR_TC_TIMELINE
+// host-side stamps of one-launch searches (debug build, BSR_HOST_TL=1): averages every 1000 calls
+#include <time.h>
+static double g_htl[8];
+static unsigned g_htl_n;
+static inline double htl_now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+static double g_htl_t[8];
+#define HTL(i) do { g_htl_t[i] = htl_now(); } while (0)
+static void htl_commit() {
+    static const bool on = getenv("BSR_HOST_TL") != nullptr;
+    if (!on) return;
+    for (int i = 1; i < 6; i++) g_htl[i] += g_htl_t[i] - g_htl_t[i - 1];
+    if (++g_htl_n == 1000) {
+        fprintf(stderr, "host timeline (us, mean of 1000): entry->impl %.2f, impl->launch %.2f, launch call %.2f, launch->result %.2f, result->return %.2f\n",
+                g_htl[1] / 1000, g_htl[2] / 1000, g_htl[3] / 1000, g_htl[4] / 1000, g_htl[5] / 1000);
+        for (double& v : g_htl) v = 0;
+        g_htl_n = 0;
+    }
+}
+#else
+#define HTL(i) do { } while (0)
+static void htl_commit() {}
+#endif
+
 static const size_t kProfPairs = 1024;
 
 static int prof_fold(bsr_store* s) {
@@ -729,27 +757,31 @@ static int launch_scan_bulk_t(bsr_store* s, const ScanArgs& a, unsigned grid, u3
     return BSR_OK;
 }
 
-// Stores of at most one panel per warp, fp32, one host query in the parameter block: scan_small_kernel.
-// Ring depth: the whole panel per live warp when that fits, else as deep as fits.
-static bool small_scan_applies(const bsr_store* s, u32 n_panels, unsigned grid, u32 K, u32* stages, u32* live) {
+// Stores of at most one panel per warp, fp32, one host query in the parameter block: scan_small_kernel,
+// 8 warps per CTA up to 8 panels per SM, 16 beyond.  Ring depth: the whole panel per live warp when that
+// fits, else as deep as fits.
+static bool small_scan_applies(const bsr_store* s, u32 n_panels, unsigned grid, u32 K, u32* stages, u32* live,
+                               u32* warps) {
     if (s->kn.no_small || is_bf16(s) || !s->param_query || s->dim > kParamQueryMax) return false;
-    if (s->dq % kChunkQuads != 0 || n_panels > grid * (u32)kBulkWarps) return false;
+    if (s->dq % kChunkQuads != 0 || n_panels > grid * 16u) return false;
+    const u32 W = n_panels <= grid * (u32)kBulkWarps ? (u32)kBulkWarps : 16u;
     const u32 cpp = s->dq / kChunkQuads;
     const u32 lv = (n_panels + grid - 1) / grid;
     u32 st = cpp;
-    while (st >= 2 && bulk_smem_bytes(s, K, st, 1, lv) + 1024 > s->smem_optin) st--;
-    if (st < 2 || lv * st > (u32)kBulkWarps * 32u) return false;
+    while (st >= 2 && bulk_smem_bytes(s, K, st, 1, lv, W) + 1024 > s->smem_optin) st--;
+    if (st < 2 || lv * st > W * 32u) return false;
     *stages = st;
     *live = lv;
+    *warps = W;
     return true;
 }
-template <bool WHOLE, int NB>
+template <int W, bool WHOLE, int NB>
 static int launch_scan_small_t(bsr_store* s, const ScanArgs& a, unsigned grid, u32 stages, u32 live, cudaStream_t st) {
     static thread_local bool configured[64] = {false};
     if (!configured[s->device & 63]) {
         cudaFuncAttributes fa;
-        CU(cudaFuncGetAttributes(&fa, scan_small_kernel<kBulkWarps, WHOLE, NB>));
-        CU(cudaFuncSetAttribute(scan_small_kernel<kBulkWarps, WHOLE, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CU(cudaFuncGetAttributes(&fa, scan_small_kernel<W, WHOLE, NB>));
+        CU(cudaFuncSetAttribute(scan_small_kernel<W, WHOLE, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(s->smem_optin - fa.sharedSizeBytes)));
         configured[s->device & 63] = true;
     }
@@ -760,29 +792,36 @@ static int launch_scan_small_t(bsr_store* s, const ScanArgs& a, unsigned grid, u
     ba.interleave = 1u;
     ba.panel_ticket = nullptr;
     // |b|: by the CTAs' idle warp when there is one (every CTA has at most `live` panels), else here
-    const bool mag_on_device = live < (u32)kBulkWarps;
+    const bool mag_on_device = live < (u32)W;
     ba.query_in_params = mag_on_device ? 2 : 1;
     memset(ba.qparam, 0, sizeof(ba.qparam));
     memcpy(ba.qparam, s->param_query, (size_t)s->dim * sizeof(float));
     ba.qparam_mag = mag_on_device ? 0.0f : host_query_magnitude(s->param_query, s->dim);
-    scan_small_kernel<kBulkWarps, WHOLE, NB>
-        <<<grid, kBulkWarps * 32, bulk_smem_bytes(s, a.k_pad, stages, 1, live), st>>>(ba);
+    HTL(2);
+    scan_small_kernel<W, WHOLE, NB><<<grid, W * 32, bulk_smem_bytes(s, a.k_pad, stages, 1, live, W), st>>>(ba);
+    HTL(3);
     s->launches++;
     CU(cudaGetLastError());
     return BSR_OK;
 }
-template <bool WHOLE>
-static int launch_scan_small_w(bsr_store* s, const ScanArgs& a, unsigned grid, u32 stages, u32 live, cudaStream_t st) {
-    // register epilogue: k_pad <= 128 with the final stage fused into the launch, at most 20 CTA lists per warp
-    const bool regs = a.fuse_final && a.k_pad <= 128 && grid <= 20u * kBulkWarps;
-    if (regs && a.k_pad == 32) return launch_scan_small_t<WHOLE, 1>(s, a, grid, stages, live, st);
-    if (regs && a.k_pad == 64) return launch_scan_small_t<WHOLE, 2>(s, a, grid, stages, live, st);
-    if (regs && a.k_pad == 128) return launch_scan_small_t<WHOLE, 4>(s, a, grid, stages, live, st);
-    return launch_scan_small_t<WHOLE, 0>(s, a, grid, stages, live, st);
-}
-static int launch_scan_small(bsr_store* s, const ScanArgs& a, unsigned grid, u32 stages, u32 live, cudaStream_t st) {
-    return stages == s->dq / kChunkQuads ? launch_scan_small_w<true>(s, a, grid, stages, live, st)
-                                         : launch_scan_small_w<false>(s, a, grid, stages, live, st);
+static int launch_scan_small(bsr_store* s, const ScanArgs& a, unsigned grid, u32 stages, u32 live, u32 warps,
+                             cudaStream_t st) {
+    // register epilogue: k_pad <= 128 with the final stage fused into the launch, at most 20 CTA lists per
+    // warp of the last CTA (16-warp CTAs: 10, and k_pad <= 64 -- registers)
+    const bool regs = a.fuse_final && a.k_pad <= 128 && grid <= 160u;
+    if (warps == 16) {
+        if (regs && a.k_pad == 32) return launch_scan_small_t<16, false, 1>(s, a, grid, stages, live, st);
+        if (regs && a.k_pad == 64) return launch_scan_small_t<16, false, 2>(s, a, grid, stages, live, st);
+        return launch_scan_small_t<16, false, 0>(s, a, grid, stages, live, st);
+    }
+    const bool whole = stages == s->dq / kChunkQuads;
+    if (regs && a.k_pad == 32)
+        return whole ? launch_scan_small_t<8, true, 1>(s, a, grid, stages, live, st) : launch_scan_small_t<8, false, 1>(s, a, grid, stages, live, st);
+    if (regs && a.k_pad == 64)
+        return whole ? launch_scan_small_t<8, true, 2>(s, a, grid, stages, live, st) : launch_scan_small_t<8, false, 2>(s, a, grid, stages, live, st);
+    if (regs && a.k_pad == 128)
+        return whole ? launch_scan_small_t<8, true, 4>(s, a, grid, stages, live, st) : launch_scan_small_t<8, false, 4>(s, a, grid, stages, live, st);
+    return whole ? launch_scan_small_t<8, true, 0>(s, a, grid, stages, live, st) : launch_scan_small_t<8, false, 0>(s, a, grid, stages, live, st);
 }
 
 template <int QB>
@@ -1177,9 +1216,9 @@ static int search_device_impl(bsr_store* s, const float* d_queries, u32 nq, u32 
         }
 #endif
         TRY(prof_begin(s, st));
-        u32 small_stages = 0, small_live = 0;
-        if (bulk && qb == 1 && small_scan_applies(s, n_panels, grid, K, &small_stages, &small_live)) {
-            TRY(launch_scan_small(s, a, grid, small_stages, small_live, st));
+        u32 small_stages = 0, small_live = 0, small_warps = 0;
+        if (bulk && qb == 1 && small_scan_applies(s, n_panels, grid, K, &small_stages, &small_live, &small_warps)) {
+            TRY(launch_scan_small(s, a, grid, small_stages, small_live, small_warps, st));
         } else if (bulk) {
             if (qb == 1 && wide) {
                 const u32 stages = bulk_stages(s, K, 1, active_warps, small_store, 16);
@@ -1331,6 +1370,7 @@ static int wait_host_ll(bsr_store* s, const volatile u64* ll, u32 seq, u32 k, ui
     };
     u32 count = 0;
     TRY(wait_word(2 * k, &count));
+    HTL(4);
     for (u32 j = 0; j < k; j++) {
         u32 v = 0;
         TRY(wait_word(j, &v));
@@ -1350,6 +1390,7 @@ static u32 next_ll_seq(bsr_store* s) {
 
 extern "C" int bsr_search(bsr_store* s, const float* queries, uint32_t nq, uint32_t k,
                           uint64_t* out_idx, float* out_dist, uint32_t* out_count) {
+    HTL(0);
     TRY(check_search_args(s, queries, nq, k, "bsr_search"));
     if (nq == 0) return BSR_OK;
     CHECK(out_idx && out_dist && out_count, BSR_ERR_INVALID, "bsr_search: null output");
@@ -1418,6 +1459,7 @@ extern "C" int bsr_search(bsr_store* s, const float* queries, uint32_t nq, uint3
         }
     }
     if (!one_launch) CU(cudaMemcpyAsync(s->d_queries.p, h, qbytes, cudaMemcpyHostToDevice, s->stream));
+    HTL(1);
     int rc = search_device_impl(s, (const float*)s->d_queries.p, nq, k, (u64*)s->d_cand.p,
                                 one_launch ? nullptr : (u64*)r, (float*)(r + ibytes), (u32*)(r + ibytes + dbytes),
                                 s->stream);
@@ -1441,6 +1483,8 @@ extern "C" int bsr_search(bsr_store* s, const float* queries, uint32_t nq, uint3
     TRY(rc);
     if (one_launch) {
         TRY(wait_host_ll(s, ll, s->ll_seq, k, out_idx, out_dist, out_count, s->scan_time_in_ll));
+        HTL(5);
+        htl_commit();
         // the kernel may still be retiring; the next call on this handle is stream-ordered behind it
         mark_idle(s);
         return BSR_OK;

@@ -1542,13 +1542,15 @@ __device__ __forceinline__ void small_epilogue(u64* lists, u32 live, u32 k, u64*
     BSR_STAMP(fo.dbg, tid == 0, 8);
     // last CTA: every warp folds its share of the CTA lists, the W partial results meet in shared memory
     u64 best[NB];
-    if (NB <= 2) {
-        if (gridDim.x <= 10u * W) fold_cta_lists_tree<NB, W, 10>(cta_keys, gridDim.x, best, warp, lane);
-        else fold_cta_lists_tree<NB, W, 20>(cta_keys, gridDim.x, best, warp, lane);  // host: gridDim.x <= 20 W
+    if (gridDim.x <= 10u * W) {
+        fold_cta_lists_tree<NB, W, 10>(cta_keys, gridDim.x, best, warp, lane);
+    } else if constexpr (NB <= 2 && W <= 8) {
+        fold_cta_lists_tree<NB, W, 20>(cta_keys, gridDim.x, best, warp, lane);  // host: gridDim.x <= 20 W
     } else {
+        // 20 lists of 4 blocks are too many registers for a tree: one list after the other
 #pragma unroll
         for (int j = 0; j < NB; j++) best[j] = kKeyMax;
-        fold_cta_lists<NB, W>(cta_keys, gridDim.x, best, warp, lane);  // too many registers for a tree: one by one
+        fold_cta_lists<NB, W>(cta_keys, gridDim.x, best, warp, lane);
     }
 #pragma unroll
     for (int j = 0; j < NB; j++) lists[(size_t)warp * K + j * 32 + lane] = best[j];

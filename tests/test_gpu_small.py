@@ -7,6 +7,7 @@ Variants by size on a 148-SM part (W = 8 warps per CTA):
   rows <= 9 472          two panels per CTA, WHOLE
   rows <= 33 152         3-7 panels per CTA, a ring of 4 KiB chunks per warp
   rows <= 37 888         8 panels per CTA: no idle warp, |b| on the host
+  rows <= 75 776         9-16 panels per CTA: 16 warps per CTA (above: the streaming kernel)
 and by top_k: k <= 32 / 64 / 128 register epilogues (NB = 1 / 2 / 4), k > 128 the generic one."""
 import numpy as np
 import pytest
@@ -31,7 +32,7 @@ def _check(eng, ref_rows, q, k, metric=0):
     return idx[0, :cnt[0]].copy(), dist[0, :cnt[0]].copy()
 
 
-@pytest.mark.parametrize("n", [1, 31, 33, 2305, 4736, 4737, 9472, 9500, 20011, 33152, 33153, 37888])
+@pytest.mark.parametrize("n", [1, 31, 33, 2305, 4736, 4737, 9472, 9500, 20011, 33152, 33153, 37888, 37889, 50000, 75776, 75777])
 @pytest.mark.parametrize("k", [1, 10, 32, 50, 100, 128, 200])
 def test_small_store_matches_the_oracle_and_the_streaming_kernel(n, k):
     rows = co.generate_rows(SEED, 0, n, 768)
