@@ -83,6 +83,7 @@ struct Knobs {
     int no_pdl = 0;          // BSR_NO_PDL: plain stream-ordered launches for back-to-back scans
     int no_mailbox = 0;      // BSR_NO_MAILBOX: cross-rank exchange through ncclAllGather only
     int no_small = 0;        // BSR_NO_SMALL: stores of one panel per warp through the streaming kernel too
+    int no_list_ll = 0;      // BSR_NO_LIST_LL: scan_small_kernel reduces its CTA lists behind a last-CTA ticket
 };
 static const Knobs& knobs() {
     static const Knobs k = [] {
@@ -110,6 +111,7 @@ static const Knobs& knobs() {
         v.no_pdl = getenv("BSR_NO_PDL") != nullptr;
         v.no_mailbox = getenv("BSR_NO_MAILBOX") != nullptr;
         v.no_small = getenv("BSR_NO_SMALL") != nullptr;
+        v.no_list_ll = getenv("BSR_NO_LIST_LL") != nullptr;
         return v;
     }();
     return k;
@@ -141,6 +143,8 @@ struct bsr_store {
     size_t smem_optin = 0;
 
     // per-search scratch (grown on demand)
+    DevBuf cta_ll;  // scan_small_kernel's self-validating CTA lists
+    u32 list_seq = 0;
     DevBuf cta_keys, merge_a, merge_b, d_queries, d_cand, d_result, d_counter, d_gtau, d_surv, d_gather, staging, ones,
         shadow, d_maxnorm, d_query1;
     // fp32 stores: bf16 copy of the rows in the tensor path's tile layout, the FILTER operand of batched
@@ -360,7 +364,7 @@ extern "C" int bsr_store_destroy(bsr_store* s) {
     DeviceGuard g(s->device);
     if (s->busy) cudaEventSynchronize(s->ev_busy);
     cudaStreamSynchronize(s->stream);
-    DevBuf* bufs[] = {&s->cta_keys, &s->merge_a, &s->merge_b, &s->d_queries,
+    DevBuf* bufs[] = {&s->cta_ll, &s->cta_keys, &s->merge_a, &s->merge_b, &s->d_queries,
                       &s->d_cand,   &s->d_result, &s->d_counter, &s->d_gtau, &s->d_surv, &s->d_gather, &s->staging, &s->ones,
                       &s->shadow,   &s->d_maxnorm, &s->d_query1};
     for (DevBuf* b : bufs)
@@ -794,6 +798,19 @@ static int launch_scan_small_t(bsr_store* s, const ScanArgs& a, unsigned grid, u
     // |b|: by the CTAs' idle warp when there is one (every CTA has at most `live` panels), else here
     const bool mag_on_device = live < (u32)W;
     ba.query_in_params = mag_on_device ? 2 : 1;
+    // self-validating CTA lists (no last-CTA ticket): register epilogue whose fold is a tree
+    ba.list_seq = 0;
+    ba.cta_ll = nullptr;
+    if (NB != 0 && NB <= 2 && !s->kn.no_list_ll) {  // (NB = 4: measured no faster than the ticket)
+        const size_t need = (size_t)grid * a.k_pad * sizeof(ulonglong2);
+        if (s->cta_ll.bytes < need) {  // fresh memory must not look like a published list
+            TRY(ensure(s->cta_ll, need));
+            CU(cudaMemsetAsync(s->cta_ll.p, 0, s->cta_ll.bytes, st));
+        }
+        s->list_seq = s->list_seq + 1 ? s->list_seq + 1 : 1;
+        ba.list_seq = s->list_seq;
+        ba.cta_ll = (ulonglong2*)s->cta_ll.p;
+    }
     memset(ba.qparam, 0, sizeof(ba.qparam));
     memcpy(ba.qparam, s->param_query, (size_t)s->dim * sizeof(float));
     ba.qparam_mag = mag_on_device ? 0.0f : host_query_magnitude(s->param_query, s->dim);
@@ -2114,6 +2131,7 @@ extern "C" int bsr_store_set_option(bsr_store* s, const char* name, int64_t valu
         {"wide", &s->kn.wide},                 {"no_tickets", &s->kn.no_tickets},
         {"no_param_query", &s->kn.no_param_query}, {"no_f32_tensor", &s->kn.no_f32_tensor},
         {"no_mailbox", &s->kn.no_mailbox},     {"no_small", &s->kn.no_small},
+        {"no_list_ll", &s->kn.no_list_ll},
     };
     for (auto& t : table)
         if (strcmp(t.name, name) == 0) {

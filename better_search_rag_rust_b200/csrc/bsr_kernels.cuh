@@ -457,6 +457,11 @@ __device__ __forceinline__ ulonglong2 ld_volatile_v2(const ulonglong2* p) {
     asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ u64 ld_volatile_u64(const unsigned long long* p) {
+    u64 v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_volatile_v2(ulonglong2* p, u64 x, u64 y) {
     asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(x), "l"(y) : "memory");
 }
@@ -1029,6 +1034,9 @@ struct BulkScanArgs {
     // ... and its magnitude |b| (src/metrics.rs:155, the same sequential fold, done once on the host)
     // so that no warp runs the second 768-step chain next to its first panel's dot products.
     float qparam_mag;
+    // scan_small_kernel, register epilogue: CTA lists as {key, list_seq} pairs (small_epilogue); 0: ticket
+    u32 list_seq;
+    ulonglong2* cta_ll;
     alignas(16) float qparam[768];  // zero-padded by the host (read as float4 by scan_small_kernel)
 };
 constexpr u32 kParamQueryMax = 768;
@@ -1503,11 +1511,52 @@ __device__ __forceinline__ void fold_cta_lists_tree(const u64* src, u32 n_lists,
     for (int j = 0; j < NB; j++) best[j] = t[0][j];
 }
 
+// The same over self-validating lists ({key, sequence number} pairs, see small_epilogue): every entry is
+// polled until it carries this search's number -- no ticket, no fence, the data IS the signal.
+template <int NB, int W, int N>
+__device__ __forceinline__ void fold_cta_lists_tree_ll(const ulonglong2* src, u32 n_lists, u32 seq, u64 (&best)[NB],
+                                                       int warp, int lane) {
+    constexpr u32 K = NB * 32;
+    u64 t[N][NB];
+    // phase 1: every sequence word of my lists, all loads in flight together, until all of them match (a
+    // 16-byte store arrives whole: a matching sequence word means the key beside it is this search's)
+    while (true) {
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+#pragma unroll
+            for (int j = 0; j < NB; j++) {
+                const u32 l = (u32)warp + (u32)i * W;
+                // (a list this warp does not have: CTA 0's own, which always exists, stands in for it)
+                const u64 y = ld_volatile_u64(&src[(size_t)(l < n_lists ? l : 0u) * K + j * 32 + lane].y);
+                ok &= y == (u64)seq;
+            }
+        }
+        if (__all_sync(0xFFFFFFFFu, ok)) break;
+    }
+    // phase 2: the keys
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+            const u32 l = (u32)warp + (u32)i * W;
+            t[i][j] = l < n_lists ? ld_volatile_u64(&src[(size_t)l * K + j * 32 + lane].x) : kKeyMax;
+        }
+    }
+    merge_tree_regs<NB, N>(t, lane);
+#pragma unroll
+    for (int j = 0; j < NB; j++) best[j] = t[0][j];
+}
+
 // lists: shared memory, on entry [W][32] -- warp w's 32 keys, ascending (warps >= live: unused) -- and W*K
 // keys of room.  Same contract as scan_epilogue<W, 1> for K = NB*32 <= 128 with the final stage fused.
+// cta_ll / list_seq (list_seq != 0, final stage fused): the CTA lists are published as {key, list_seq}
+// pairs and CTA 0 -- every CTA of the grid is resident, one per SM -- polls them: the last-CTA ticket costs
+// a store -> fence -> atomic -> load chain of three L2 round trips between the slowest CTA's list and its
+// first use, this costs one.
 template <int W, int NB>
 __device__ __forceinline__ void small_epilogue(u64* lists, u32 live, u32 k, u64* cta_keys, const FinalOut& fo,
-                                               bool fuse_final) {
+                                               bool fuse_final, ulonglong2* cta_ll, u32 list_seq) {
     constexpr u32 K = NB * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ u32 s_is_last;
@@ -1521,9 +1570,14 @@ __device__ __forceinline__ void small_epilogue(u64* lists, u32 live, u32 k, u64*
             for (int j = 1; j < NB; j++) t[w][j] = kKeyMax;
         }
         if (live > 1) merge_tree_regs<NB, W>(t, lane);
+        if (list_seq) {
 #pragma unroll
-        for (int j = 0; j < NB; j++) cta_keys[(size_t)blockIdx.x * K + j * 32 + lane] = t[0][j];
-        if (fuse_final) {
+            for (int j = 0; j < NB; j++) st_volatile_v2(cta_ll + (size_t)blockIdx.x * K + j * 32 + lane, t[0][j], (u64)list_seq);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NB; j++) cta_keys[(size_t)blockIdx.x * K + j * 32 + lane] = t[0][j];
+        }
+        if (fuse_final && !list_seq) {
             // release: the stores above (ordered before lane 0's atomic by the warp barrier) are visible to
             // whoever reads the counter's final value; acquire: the last CTA sees every other CTA's list
             __syncwarp();
@@ -1536,13 +1590,23 @@ __device__ __forceinline__ void small_epilogue(u64* lists, u32 live, u32 k, u64*
     }
     BSR_STAMP(fo.dbg, blockIdx.x == 0 && tid == 0, 6);
     if (!fuse_final) return;
-    __syncthreads();
-    BSR_STAMP(fo.dbg, blockIdx.x == 0 && tid == 0, 7);
-    if (!s_is_last) return;
+    if (list_seq) {
+        if (blockIdx.x != 0) return;
+    } else {
+        __syncthreads();
+        BSR_STAMP(fo.dbg, blockIdx.x == 0 && tid == 0, 7);
+        if (!s_is_last) return;
+    }
     BSR_STAMP(fo.dbg, tid == 0, 8);
-    // last CTA: every warp folds its share of the CTA lists, the W partial results meet in shared memory
+    // last CTA (or CTA 0): every warp folds its share of the CTA lists, the W partial results meet in shared memory
     u64 best[NB];
-    if (gridDim.x <= 10u * W) {
+    if (NB <= 2 && list_seq) {  // host: only with NB <= 2
+        if constexpr (NB <= 2) {
+            if (gridDim.x <= 10u * W) fold_cta_lists_tree_ll<NB, W, 10>(cta_ll, gridDim.x, list_seq, best, warp, lane);
+            else if constexpr (W <= 8) fold_cta_lists_tree_ll<NB, W, 20>(cta_ll, gridDim.x, list_seq, best, warp, lane);
+        }
+        __syncthreads();  // warp 0 has read the per-warp lists this CTA's partial results overwrite
+    } else if (gridDim.x <= 10u * W) {
         fold_cta_lists_tree<NB, W, 10>(cta_keys, gridDim.x, best, warp, lane);
     } else if constexpr (NB <= 2 && W <= 8) {
         fold_cta_lists_tree<NB, W, 20>(cta_keys, gridDim.x, best, warp, lane);  // host: gridDim.x <= 20 W
@@ -1581,7 +1645,7 @@ __device__ __forceinline__ void small_epilogue(u64* lists, u32 live, u32 k, u64*
                 const unsigned m = __ballot_sync(0xFFFFFFFFu, (u32)lane < fo.ll_k && v != kKeyMax);
                 if (lane == 0) ll_publish_count(fo, (u32)__popc(m));
             }
-            if (lane == 0) *fo.done_counter = 0;
+            if (lane == 0 && !list_seq) *fo.done_counter = 0;
         } else {
             // 32 < K <= 128: the final list goes on through shared memory (the cross-rank exchange is
             // CTA-wide); it overwrites partial list 0, which only this warp has read
@@ -1621,7 +1685,7 @@ __device__ __forceinline__ void small_epilogue(u64* lists, u32 live, u32 k, u64*
     if (tid == 0) {
         if (fo.idx) fo.count[0] = s_cnt[0][0] + s_cnt[0][1] + s_cnt[0][2] + s_cnt[0][3];
         if (fo.host_ll) ll_publish_count(fo, s_cnt[1][0] + s_cnt[1][1] + s_cnt[1][2] + s_cnt[1][3]);
-        *fo.done_counter = 0;
+        if (!list_seq) *fo.done_counter = 0;
     }
     BSR_STAMP(fo.dbg, tid == 0, 10);
 }
@@ -1688,9 +1752,19 @@ __global__ void __launch_bounds__(W * 32, 1) scan_small_kernel(const __grid_cons
     // the query, zero-padded to the padded column count (parameter block: the host guarantees it)
     // (one 16-byte constant load per thread: per-lane addresses in the constant bank are served one by
     // one, and four scalar loads per thread made this loop 1.3 us of a 20 us search)
-    for (u32 j = tid; j < dq; j += (W * 32)) sq[j] = reinterpret_cast<const float4*>(ba.qparam)[j];
-    BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 15);
+    // Reading the parameter block is slow when it is cold (~0.8 us for the whole query, every launch): with
+    // enough idle warps (`prog`) only the first four chunks' columns are staged before the scan warps start
+    // -- 32/W lanes of every warp, so that no warp waits for more than one constant-cache line -- and the
+    // idle warps stage the rest next to the first four chunks' adds (named barrier 1, see the loop).
+    const float4* qp4 = reinterpret_cast<const float4*>(ba.qparam);
     const bool has = (u32)warp < live;
+    const bool prog = live <= 3 && cpp > 4;
+    if (prog) {
+        if (lane < 32 / W) sq[warp * (32 / W) + lane] = qp4[warp * (32 / W) + lane];
+    } else {
+        for (u32 j = tid; j < dq; j += (W * 32)) sq[j] = qp4[j];
+    }
+    BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 15);
     const u32 panel = (u32)warp * gridDim.x + blockIdx.x;
     const u32 row = panel * kPanelRows + lane;
     const bool valid = has && row < a.n_rows;
@@ -1709,6 +1783,11 @@ __global__ void __launch_bounds__(W * 32, 1) scan_small_kernel(const __grid_cons
     __shared__ float s_mag_b;
     float acc_out = 0.0f;
     bool maybe_out = false;
+    if (prog && !has) {  // the rest of the query, by the warps without a panel
+        for (u32 j = 32 + ((u32)warp - live) * 32 + lane; j < dq; j += (W - live) * 32) sq[j] = qp4[j];
+        if (warp == W - 1) asm volatile("bar.sync 1, %0;" ::"n"(W * 32) : "memory");  // it reads the whole query next
+        else asm volatile("bar.arrive 1, %0;" ::"n"(W * 32) : "memory");
+    }
     if (!has && ba.query_in_params == 2 && warp == W - 1) {
         // |b| (src/metrics.rs:155, the same sequential fold) by a warp that has no panel: the host would
         // spend ~1.3 us on these 768 dependent adds before it could launch; here they run next to the scan
@@ -1785,6 +1864,8 @@ __global__ void __launch_bounds__(W * 32, 1) scan_small_kernel(const __grid_cons
 #ifdef BSR_TC_TIMELINE
             if (a.dbg && blockIdx.x == 0 && tid == 0 && c < 24) s_tl[2 * c] = s_tl[2 * c + 1] = (u32)clock64();
 #endif
+            // (the columns of chunks 4 and up: staged by the idle warps meanwhile)
+            if (prog && c == 3) asm volatile("bar.sync 1, %0;" ::"n"(W * 32) : "memory");
             while (!ok) ok = mbar_try_wait_u32(bar0 + s1 * 8, p1);
             acc = __uint_as_float(__float_as_uint(acc) | (ok ^ 1u));
             const u32 ok2 = mbar_try_wait_u32(bar0 + s2 * 8, p2);
@@ -1850,7 +1931,7 @@ __global__ void __launch_bounds__(W * 32, 1) scan_small_kernel(const __grid_cons
     }
     __syncthreads();
     BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 5);
-    if constexpr (NB != 0) small_epilogue<W, NB>(lists, live, a.k, a.cta_keys, a.fin, a.fuse_final != 0);
+    if constexpr (NB != 0) small_epilogue<W, NB>(lists, live, a.k, a.cta_keys, a.fin, a.fuse_final != 0, ba.cta_ll, ba.list_seq);
     else scan_epilogue<W, 1>(lists, K, a.k, a.cta_keys, a.fin, a.fuse_final != 0, nullptr, live);
 }
 
