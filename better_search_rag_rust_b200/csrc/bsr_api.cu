@@ -766,11 +766,12 @@ static int launch_scan_bulk_t(bsr_store* s, const ScanArgs& a, unsigned grid, u3
 // fits, else as deep as fits.
 static bool small_scan_applies(const bsr_store* s, u32 n_panels, unsigned grid, u32 K, u32* stages, u32* live,
                                u32* warps) {
-    if (s->kn.no_small || is_bf16(s) || !s->param_query || s->dim > kParamQueryMax) return false;
+    if (s->kn.no_small || is_bf16(s) || (s->param_query && s->dim > kParamQueryMax)) return false;
     if (s->dq % kChunkQuads != 0 || n_panels > grid * 16u) return false;
     const u32 W = n_panels <= grid * (u32)kBulkWarps ? (u32)kBulkWarps : 16u;
     const u32 cpp = s->dq / kChunkQuads;
     const u32 lv = (n_panels + grid - 1) / grid;
+    if (!s->param_query && lv == W) return false;  // a device query needs an idle warp for |b|
     u32 st = cpp;
     while (st >= 2 && bulk_smem_bytes(s, K, st, 1, lv, W) + 1024 > s->smem_optin) st--;
     if (st < 2 || lv * st > W * 32u) return false;
@@ -797,7 +798,7 @@ static int launch_scan_small_t(bsr_store* s, const ScanArgs& a, unsigned grid, u
     ba.panel_ticket = nullptr;
     // |b|: by the CTAs' idle warp when there is one (every CTA has at most `live` panels), else here
     const bool mag_on_device = live < (u32)W;
-    ba.query_in_params = mag_on_device ? 2 : 1;
+    ba.query_in_params = !s->param_query ? 0 : mag_on_device ? 2 : 1;
     // self-validating CTA lists (no last-CTA ticket): register epilogue whose fold is a tree
     ba.list_seq = 0;
     ba.cta_ll = nullptr;
@@ -811,8 +812,10 @@ static int launch_scan_small_t(bsr_store* s, const ScanArgs& a, unsigned grid, u
         ba.list_seq = s->list_seq;
         ba.cta_ll = (ulonglong2*)s->cta_ll.p;
     }
-    memset(ba.qparam, 0, sizeof(ba.qparam));
-    memcpy(ba.qparam, s->param_query, (size_t)s->dim * sizeof(float));
+    if (s->param_query) {
+        memset(ba.qparam, 0, sizeof(ba.qparam));
+        memcpy(ba.qparam, s->param_query, (size_t)s->dim * sizeof(float));
+    }
     ba.qparam_mag = mag_on_device ? 0.0f : host_query_magnitude(s->param_query, s->dim);
     HTL(2);
     scan_small_kernel<W, WHOLE, NB><<<grid, W * 32, bulk_smem_bytes(s, a.k_pad, stages, 1, live, W), st>>>(ba);

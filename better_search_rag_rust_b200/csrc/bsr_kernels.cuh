@@ -1028,8 +1028,9 @@ struct BulkScanArgs {
     // Zero before the launch; the last CTA to finish resets it (needs ScanArgs::fin.done_counter).
     u32* panel_ticket;
     // Single host query (bsr_search, dim <= kParamQueryMax): the query travels in the kernel's
-    // parameter block (constant bank) instead of a separate host-to-device copy.  2 (scan_small_kernel
-    // only): ... and qparam_mag is not set, a warp without a panel computes |b|.
+    // parameter block (constant bank) instead of a separate host-to-device copy.  scan_small_kernel only:
+    // 2: ... and qparam_mag is not set, a warp without a panel computes |b|; 0: the query is ScanArgs::query
+    // (device memory), |b| likewise.
     u32 query_in_params;
     // ... and its magnitude |b| (src/metrics.rs:155, the same sequential fold, done once on the host)
     // so that no warp runs the second 768-step chain next to its first panel's dot products.
@@ -1756,13 +1757,24 @@ __global__ void __launch_bounds__(W * 32, 1) scan_small_kernel(const __grid_cons
     // enough idle warps (`prog`) only the first four chunks' columns are staged before the scan warps start
     // -- 32/W lanes of every warp, so that no warp waits for more than one constant-cache line -- and the
     // idle warps stage the rest next to the first four chunks' adds (named barrier 1, see the loop).
-    const float4* qp4 = reinterpret_cast<const float4*>(ba.qparam);
+    // (query_in_params == 0: a query in device memory -- bsr_search_device -- read column by column, it
+    // need not be 16-byte aligned; |b| then always comes from the idle warp, the host guarantees there is one)
+    auto query_quad = [&](u32 j) -> float4 {
+        if (ba.query_in_params) return reinterpret_cast<const float4*>(ba.qparam)[j];
+        const u32 c = 4 * j;
+        float4 v;
+        v.x = (c + 0 < a.dim) ? __ldg(a.query + c + 0) : 0.0f;
+        v.y = (c + 1 < a.dim) ? __ldg(a.query + c + 1) : 0.0f;
+        v.z = (c + 2 < a.dim) ? __ldg(a.query + c + 2) : 0.0f;
+        v.w = (c + 3 < a.dim) ? __ldg(a.query + c + 3) : 0.0f;
+        return v;
+    };
     const bool has = (u32)warp < live;
     const bool prog = live <= 3 && cpp > 4;
     if (prog) {
-        if (lane < 32 / W) sq[warp * (32 / W) + lane] = qp4[warp * (32 / W) + lane];
+        if (lane < 32 / W) sq[warp * (32 / W) + lane] = query_quad(warp * (32 / W) + lane);
     } else {
-        for (u32 j = tid; j < dq; j += (W * 32)) sq[j] = qp4[j];
+        for (u32 j = tid; j < dq; j += (W * 32)) sq[j] = query_quad(j);
     }
     BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 15);
     const u32 panel = (u32)warp * gridDim.x + blockIdx.x;
@@ -1784,11 +1796,11 @@ __global__ void __launch_bounds__(W * 32, 1) scan_small_kernel(const __grid_cons
     float acc_out = 0.0f;
     bool maybe_out = false;
     if (prog && !has) {  // the rest of the query, by the warps without a panel
-        for (u32 j = 32 + ((u32)warp - live) * 32 + lane; j < dq; j += (W - live) * 32) sq[j] = qp4[j];
+        for (u32 j = 32 + ((u32)warp - live) * 32 + lane; j < dq; j += (W - live) * 32) sq[j] = query_quad(j);
         if (warp == W - 1) asm volatile("bar.sync 1, %0;" ::"n"(W * 32) : "memory");  // it reads the whole query next
         else asm volatile("bar.arrive 1, %0;" ::"n"(W * 32) : "memory");
     }
-    if (!has && ba.query_in_params == 2 && warp == W - 1) {
+    if (!has && ba.query_in_params != 1 && warp == W - 1) {
         // |b| (src/metrics.rs:155, the same sequential fold) by a warp that has no panel: the host would
         // spend ~1.3 us on these 768 dependent adds before it could launch; here they run next to the scan
         float qs = 0.0f;
@@ -1920,7 +1932,7 @@ __global__ void __launch_bounds__(W * 32, 1) scan_small_kernel(const __grid_cons
         maybe_out = maybe;
     }
     float mag_b = ba.qparam_mag;
-    if (ba.query_in_params == 2) {  // |b| from this CTA's idle warp (below)
+    if (ba.query_in_params != 1) {  // |b| from this CTA's idle warp (above)
         __syncthreads();
         mag_b = s_mag_b;
     }

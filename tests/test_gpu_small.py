@@ -48,6 +48,14 @@ def test_small_store_matches_the_oracle_and_the_streaming_kernel(n, k):
     got = [_check(eng, rows, q, k) for q in queries]
     if n > 40 and k >= 2:
         assert got[0][0][:2].tolist() == [7, n // 2] and got[0][1][0] == 0.0 and got[0][1][1] == 0.0
+    # the same kernel with the query in device memory (bsr_search_device; above 8 panels per SM with no idle
+    # warp for |b| that is the streaming kernel): same candidates
+    import torch
+    from better_search_rag_rust_b200 import search as S
+    for q, (gi, gd) in zip(queries, got):
+        cand = eng.search_candidates(torch.from_numpy(q).cuda().reshape(1, -1), k)
+        ci, cd = S.unpack_candidates(cand.cpu().numpy().view(np.uint64)[0], k)
+        assert ci.tolist() == gi.tolist() and _bits(cd).tolist() == _bits(gd).tolist()
     st.set_option("no_small", 1)                     # the streaming kernel on the same store: same answers
     for q, (gi, gd) in zip(queries, got):
         idx, dist, cnt = eng.local_top_k(q.reshape(1, -1), k)
