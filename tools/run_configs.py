@@ -44,11 +44,29 @@ def single_query(name, n, k, dtype="f32", reps=200, cpu=False):
     t0 = time.perf_counter()
     for _ in range(reps):
         idx, dist, cnt = eng.local_top_k(q_np, k)
-    e2e_ms = (time.perf_counter() - t0) / reps * 1e3
+    py_ms = (time.perf_counter() - t0) / reps * 1e3
     assert idx[0, 0] == 0 and dist[0, 0] == 0.0
+    # the C ABI itself (what a Rust / C++ caller pays): bsr_search on preallocated host buffers, per-call
+    # wall clock, median -- the Python wrapper above adds ~10 us of numpy / ctypes work per call
+    from better_search_rag_rust_b200 import _lib
+    L = _lib.lib()
+    qh = np.ascontiguousarray(q_np.reshape(1, -1), dtype=np.float32)
+    oi, od, oc = np.zeros((1, k), np.uint64), np.zeros((1, k), np.float32), np.zeros(1, np.uint32)
+    cargs = (st.handle, qh.ctypes.data, 1, k, oi.ctypes.data, od.ctypes.data, oc.ctypes.data)
+    for _ in range(20):
+        L.bsr_search(*cargs)
+    t = []
+    for _ in range(max(reps, 500)):
+        t0 = time.perf_counter_ns()
+        L.bsr_search(*cargs)
+        t.append(time.perf_counter_ns() - t0)
+    e2e_ms = float(np.median(t)) / 1e6
+    assert oi[0, 0] == 0 and od[0, 0] == 0.0 and oc[0] == k
     r = {"rows": n, "dtype": dtype, "k": k, "ms_per_query": ms, "queries_per_s": 1e3 / ms,
          "scan_kernel_ms": scan_ms / n_scans, "scan_GBps": st.scan_bytes() / (scan_ms / n_scans) / 1e6,
-         "e2e_ms_per_query": e2e_ms, "e2e_queries_per_s": 1e3 / e2e_ms}
+         "e2e_ms_per_query": e2e_ms, "e2e_queries_per_s": 1e3 / e2e_ms,
+         "e2e_path": "bsr_search (C ABI, host buffers), median of per-call wall clock",
+         "e2e_ms_per_query_python_wrapper": py_ms}
     if cpu:
         rows = co.generate_rows(SEED, 0, n, 768)
         for threads in (1, 16):
@@ -86,6 +104,7 @@ single_query("extra_1M_bf16_k10_exact", 1_000_000, 10, dtype="bf16")
 for k in (1, 50, 100, 256, 1024):
     single_query(f"config5_ksweep_1M_fp32_k{k}", 1_000_000, k, reps=100)
 single_query("config0c_2305_fp32_k50_reference_store", 2305, 50, reps=500)
+single_query("config0d_2305_fp32_k10_reference_store", 2305, 10, reps=500)
 batches("config5_batch_sweep_1M_fp32_k10", 1_000_000, 10, "f32", [1, 2, 4, 8, 16, 32, 64, 256, 1024, 4096])
 batches("config5_batch_sweep_1M_bf16_k10", 1_000_000, 10, "bf16", [1, 8, 32, 128, 1024, 4096])
 batches("config5_k_sweep_1M_bf16_256_queries", 1_000_000, 1024, "bf16", [256])
