@@ -996,6 +996,14 @@ __device__ __forceinline__ u64 make_evict_first_policy() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+// A store a few times the size of L2, scanned again and again: `keep` of its lines (chosen by address,
+// so the same ones every launch) ask to stay in L2, the others to leave first -- instead of every scan
+// streaming the whole store from HBM through a cache that never holds what the next scan reads first.
+__device__ __forceinline__ u64 make_keep_fraction_policy(float keep) {
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol) : "f"(keep));
+    return pol;
+}
 // global -> shared bulk copy (TMA, 1-D), completion counted in bytes on `bar`
 __device__ __forceinline__ void bulk_g2s(u32 dst, const void* src, u32 bytes, u32 bar, u64 policy) {
     asm volatile(
@@ -1038,6 +1046,8 @@ struct BulkScanArgs {
     // scan_small_kernel, register epilogue: CTA lists as {key, list_seq} pairs (small_epilogue); 0: ticket
     u32 list_seq;
     ulonglong2* cta_ll;
+    // fraction of the store's lines that ask to stay in L2 (make_keep_fraction_policy); 0: plain evict-first
+    float l2_keep;
     alignas(16) float qparam[768];  // zero-padded by the host (read as float4 by scan_small_kernel)
 };
 constexpr u32 kParamQueryMax = 768;
@@ -1084,7 +1094,7 @@ __global__ void __launch_bounds__(W * 32, 1) scan_topk_bulk_kernel(const __grid_
     const u32 KB = dq >> 4;                                      // bf16: 64-column blocks
     const u32 cpp = BF16 ? KB : (dq + CH - 1) / CH;              // chunks per 32-row panel
     const size_t panel_stride = (size_t)dq * 32;                 // fp32 layout, float4 units
-    const u64 policy = make_evict_first_policy();
+    const u64 policy = ba.l2_keep > 0.0f ? make_keep_fraction_policy(ba.l2_keep) : make_evict_first_policy();
     const bool dyn = ba.panel_ticket != nullptr;                 // host: only with S <= cpp (see below)
     const u32 first_ticket_panel = gridDim.x * W;
 
@@ -1731,7 +1741,7 @@ __global__ void __launch_bounds__(W * 32, 1) scan_small_kernel(const __grid_cons
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // this CTA's panels are blockIdx.x, blockIdx.x + gridDim.x, ...: warp w owns the w-th of them
     const u32 live = min((a.n_panels - 1 - blockIdx.x) / gridDim.x + 1, (u32)W);
-    const u64 policy = make_evict_first_policy();
+    const u64 policy = ba.l2_keep > 0.0f ? make_keep_fraction_policy(ba.l2_keep) : make_evict_first_policy();
 
     // First ring fill: request r = (slot, warp), slot-major so that every warp's chunk 0 is asked for
     // first; thread (warp r % W, lane r / W) initialises the request's barrier, arms it and issues the copy
