@@ -1508,12 +1508,13 @@ __device__ __forceinline__ void merge_tree_regs(u64 (&t)[N][NB], int lane) {
 }
 // this warp's share (lists warp, warp + W, ...) of the n_lists CTA lists in global memory -> best
 template <int NB, int W, int N>
-__device__ __forceinline__ void fold_cta_lists_tree(const u64* src, u32 n_lists, u64 (&best)[NB], int warp, int lane) {
+__device__ __forceinline__ void fold_cta_lists_tree(const u64* src, u32 n_lists, u64 (&best)[NB], int warp, int lane,
+                                                    u32 first = 0) {
     constexpr u32 K = NB * 32;
     u64 t[N][NB];
 #pragma unroll
     for (int i = 0; i < N; i++) {  // every load first: one L2 round trip
-        const u32 l = (u32)warp + (u32)i * W;
+        const u32 l = (u32)warp + (first + (u32)i) * W;
 #pragma unroll
         for (int j = 0; j < NB; j++) t[i][j] = l < n_lists ? ldcg_u64(src + (size_t)l * K + j * 32 + lane) : kKeyMax;
     }
@@ -1559,6 +1560,33 @@ __device__ __forceinline__ void fold_cta_lists_tree_ll(const ulonglong2* src, u3
     for (int j = 0; j < NB; j++) best[j] = t[0][j];
 }
 
+// The same tree across the warps of a CTA, through shared memory (16-warp CTAs: sixteen lists per lane
+// do not fit their 128 registers): `n` ascending NB*32-key lists at base + i*stride -> warp 0's registers
+// (and base).  Level by level, one merge per warp, a CTA barrier between levels.  Every thread of the
+// CTA must call it.
+template <int NB>
+__device__ __forceinline__ void merge_tree_smem(u64* base, u32 stride, u32 n, u64 (&out)[NB], int warp, int lane) {
+    for (u32 s = 1; s < n; s <<= 1) {
+        __syncthreads();
+        if ((u32)warp < (n + 2 * s - 1) / (2 * s) && (2 * s * warp + s) < n) {
+            u64* pa = base + (size_t)(2 * s * warp) * stride;
+            const u64* pb = base + (size_t)(2 * s * warp + s) * stride;
+            u64 a[NB], b[NB];
+#pragma unroll
+            for (int j = 0; j < NB; j++) {
+                a[j] = pa[j * 32 + lane];
+                b[j] = pb[j * 32 + lane];
+            }
+            merge_keep<NB>(a, b, lane);
+#pragma unroll
+            for (int j = 0; j < NB; j++) pa[j * 32 + lane] = a[j];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NB; j++) out[j] = base[j * 32 + lane];
+}
+
 // lists: shared memory, on entry [W][32] -- warp w's 32 keys, ascending (warps >= live: unused) -- and W*K
 // keys of room.  Same contract as scan_epilogue<W, 1> for K = NB*32 <= 128 with the final stage fused.
 // cta_ll / list_seq (list_seq != 0, final stage fused): the CTA lists are published as {key, list_seq}
@@ -1571,8 +1599,21 @@ __device__ __forceinline__ void small_epilogue(u64* lists, u32 live, u32 k, u64*
     constexpr u32 K = NB * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ u32 s_is_last;
-    if (warp == 0) {
-        // the CTA's best K: this CTA's per-warp lists (one block each), padded with empty blocks
+    u64 mine[NB];  // (warp 0) the CTA's best K: this CTA's per-warp lists, one block each
+    if constexpr (W > 8) {
+        // pairs of 32-key lists first (in place: a pair's two lists make room for one K-key list, K <= 64),
+        // then the tree over the W/2 results
+        static_assert(W <= 8 || NB <= 2, "16-warp CTAs: top_k <= 64 in the register epilogue");
+        if (warp < W / 2) {
+            const u64 a = (u32)(2 * warp) < live ? lists[(2 * warp) * 32 + lane] : kKeyMax;
+            u64 b = (u32)(2 * warp + 1) < live ? lists[(2 * warp + 1) * 32 + lane] : kKeyMax;
+            __syncwarp();
+            const u64 lo = warp_merge_split32(a, b, lane);  // b: the upper 32
+            lists[(size_t)warp * 64 + lane] = lo;
+            if (NB > 1) lists[(size_t)warp * 64 + 32 + lane] = b;
+        }
+        merge_tree_smem<NB>(lists, 64, W / 2, mine, warp, lane);
+    } else if (warp == 0) {
         u64 t[W][NB];
 #pragma unroll
         for (int w = 0; w < W; w++) {
@@ -1581,12 +1622,16 @@ __device__ __forceinline__ void small_epilogue(u64* lists, u32 live, u32 k, u64*
             for (int j = 1; j < NB; j++) t[w][j] = kKeyMax;
         }
         if (live > 1) merge_tree_regs<NB, W>(t, lane);
+#pragma unroll
+        for (int j = 0; j < NB; j++) mine[j] = t[0][j];
+    }
+    if (warp == 0) {
         if (list_seq) {
 #pragma unroll
-            for (int j = 0; j < NB; j++) st_volatile_v2(cta_ll + (size_t)blockIdx.x * K + j * 32 + lane, t[0][j], (u64)list_seq);
+            for (int j = 0; j < NB; j++) st_volatile_v2(cta_ll + (size_t)blockIdx.x * K + j * 32 + lane, mine[j], (u64)list_seq);
         } else {
 #pragma unroll
-            for (int j = 0; j < NB; j++) cta_keys[(size_t)blockIdx.x * K + j * 32 + lane] = t[0][j];
+            for (int j = 0; j < NB; j++) cta_keys[(size_t)blockIdx.x * K + j * 32 + lane] = mine[j];
         }
         if (fuse_final && !list_seq) {
             // release: the stores above (ordered before lane 0's atomic by the warp barrier) are visible to
@@ -1621,8 +1666,13 @@ __device__ __forceinline__ void small_epilogue(u64* lists, u32 live, u32 k, u64*
         fold_cta_lists_tree<NB, W, 10>(cta_keys, gridDim.x, best, warp, lane);
     } else if constexpr (NB <= 2 && W <= 8) {
         fold_cta_lists_tree<NB, W, 20>(cta_keys, gridDim.x, best, warp, lane);  // host: gridDim.x <= 20 W
+    } else if constexpr (W <= 8) {
+        // 20 lists of 4 blocks are too many registers for one tree: two trees of 10, then one more merge
+        u64 more[NB];
+        fold_cta_lists_tree<NB, W, 10>(cta_keys, gridDim.x, best, warp, lane);
+        fold_cta_lists_tree<NB, W, 10>(cta_keys, gridDim.x, more, warp, lane, 10);
+        merge_keep<NB>(best, more, lane);
     } else {
-        // 20 lists of 4 blocks are too many registers for a tree: one list after the other
 #pragma unroll
         for (int j = 0; j < NB; j++) best[j] = kKeyMax;
         fold_cta_lists<NB, W>(cta_keys, gridDim.x, best, warp, lane);
@@ -1631,7 +1681,10 @@ __device__ __forceinline__ void small_epilogue(u64* lists, u32 live, u32 k, u64*
     for (int j = 0; j < NB; j++) lists[(size_t)warp * K + j * 32 + lane] = best[j];
     __syncthreads();
     BSR_STAMP(fo.dbg, tid == 0, 9);
-    if (warp == 0) {
+    u64 fin[NB];  // (warp 0) the shard's best K
+    if constexpr (W > 8) {
+        merge_tree_smem<NB>(lists, K, W, fin, warp, lane);
+    } else if (warp == 0) {
         u64 t[W][NB];
 #pragma unroll
         for (int w = 0; w < W; w++) {
@@ -1639,8 +1692,12 @@ __device__ __forceinline__ void small_epilogue(u64* lists, u32 live, u32 k, u64*
             for (int j = 0; j < NB; j++) t[w][j] = lists[(size_t)w * K + j * 32 + lane];
         }
         merge_tree_regs<NB, W>(t, lane);
+#pragma unroll
+        for (int j = 0; j < NB; j++) fin[j] = t[0][j];
+    }
+    if (warp == 0) {
         if (NB == 1) {
-            const u64 v = mailbox_exchange32(t[0][0], fo.mb, k, lane);  // multi-rank: send to root / fold the peers in
+            const u64 v = mailbox_exchange32(fin[0], fo.mb, k, lane);  // multi-rank: send to root / fold the peers in
             fo.keys[lane] = (u32)lane < k ? v : kKeyMax;  // slots past top_k are published empty
             if (fo.idx) {
                 const bool ok = (u32)lane < k && v != kKeyMax;
@@ -1661,7 +1718,7 @@ __device__ __forceinline__ void small_epilogue(u64* lists, u32 live, u32 k, u64*
             // 32 < K <= 128: the final list goes on through shared memory (the cross-rank exchange is
             // CTA-wide); it overwrites partial list 0, which only this warp has read
 #pragma unroll
-            for (int j = 0; j < NB; j++) lists[j * 32 + lane] = t[0][j];
+            for (int j = 0; j < NB; j++) lists[j * 32 + lane] = fin[j];
         }
     }
     if (NB == 1) {
