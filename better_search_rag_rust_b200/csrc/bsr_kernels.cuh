@@ -1817,15 +1817,14 @@ __global__ void __launch_bounds__(W * 32, 1) scan_small_kernel(const __grid_cons
         }
     }
     BSR_STAMP(a.dbg, blockIdx.x == 0 && tid == 0, 14);
-    // the query, zero-padded to the padded column count (parameter block: the host guarantees it)
-    // (one 16-byte constant load per thread: per-lane addresses in the constant bank are served one by
-    // one, and four scalar loads per thread made this loop 1.3 us of a 20 us search)
-    // Reading the parameter block is slow when it is cold (~0.8 us for the whole query, every launch): with
-    // enough idle warps (`prog`) only the first four chunks' columns are staged before the scan warps start
-    // -- 32/W lanes of every warp, so that no warp waits for more than one constant-cache line -- and the
-    // idle warps stage the rest next to the first four chunks' adds (named barrier 1, see the loop).
-    // (query_in_params == 0: a query in device memory -- bsr_search_device -- read column by column, it
-    // need not be 16-byte aligned; |b| then always comes from the idle warp, the host guarantees there is one)
+    // The query into shared memory, zero-padded to the padded column count (the host pads the parameter
+    // block).  Reading a parameter block that is cold every launch is slow -- per-lane addresses in the
+    // constant bank are served one by one: 1.3 us with four scalar loads per thread, 0.8 us with one float4
+    // per thread -- so with enough idle warps (`prog`) only the first four chunks' columns are staged before
+    // the scan warps start (32/W lanes of every warp: no warp waits for more than one constant-cache line)
+    // and the warps without a panel stage the rest next to the first chunks' adds (named barrier 1, see the
+    // loop).  query_in_params == 0: a query in device memory (bsr_search_device), read column by column --
+    // it need not be 16-byte aligned; |b| then always comes from the idle warp (the host makes sure of one).
     auto query_quad = [&](u32 j) -> float4 {
         if (ba.query_in_params) return reinterpret_cast<const float4*>(ba.qparam)[j];
         const u32 c = 4 * j;

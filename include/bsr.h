@@ -237,7 +237,8 @@ BSR_API int bsr_store_set_tensor_min_batch(bsr_store *store, uint32_t min_batch)
  *   "max_grid" n      cap the scan grid at n CTAs (test hook: long per-warp row streams on small stores)
  *   "bulk_stages" n   ring depth of the bulk-async scan        "max_qb" n     widest exact query group
  *   "scan_ldg" 0/1    register-staged scan kernel              "no_wide" 0/1  no 16-warp CTAs
- *   "no_fuse_wide", "tensor_mode", "tensor_stages", "tensor_stage_kb", "tc_stats", "no_pdl", "no_mailbox" */
+ *   "no_fuse_wide", "tensor_mode", "tensor_stages", "tensor_stage_kb", "tc_stats", "no_pdl", "no_mailbox",
+ *   "no_small" (small stores through the streaming kernel), "no_list_ll", "no_l2_keep" */
 BSR_API int bsr_store_set_option(bsr_store *store, const char *name, int64_t value);
 
 /* ---- introspection for the benchmark harness ---------------------------------------------- */
@@ -245,8 +246,11 @@ BSR_API int bsr_store_set_option(bsr_store *store, const char *name, int64_t val
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 BSR_API int bsr_store_launch_count(const bsr_store *store, uint64_t *n_launches);
 
-/* Device time of the most recent scan kernel on this handle, in milliseconds, from CUDA events
- * recorded on the stream the kernel was launched on (synchronises that stream). */
+/* Device time of the most recent scan stage on this handle, in milliseconds.  A search that is one
+ * fused launch answered through pinned host memory (bsr_search / bsr_search_parallel, one query,
+ * top_k <= 128) carries no events in its stream: the launch measures itself (%globaltimer of its first
+ * CTA's first instruction to the store of the result) and that duration is reported.  Every other
+ * search: CUDA events recorded on the stream the kernels were launched on (synchronises that stream). */
 BSR_API int bsr_store_last_scan_ms(bsr_store *store, float *ms);
 
 /* Per-launch timing of the scan kernel: while enabled, every scan launch is bracketed by CUDA
