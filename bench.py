@@ -13,7 +13,8 @@ slots -> on-device merge on root (weak scaling: rows per GPU fixed).
 `value` counts 12.5 M-row shard scans per second (= queries/s x N: the whole-job aggregate the
 contract asks for, proportional to rows scanned per second; at N = 1 it is plain queries/s).  The
 queries/s against the whole N-shard store is reported beside it as `queries_per_s_whole_store`.
-`extra_1m` repeats the measurement on BASELINE.json configs[1] (1 M x 768 per GPU).
+`extra_1m` repeats the measurement on BASELINE.json configs[1] (1 M x 768 per GPU);
+`extra_small_stores` is the latency of one search on 2 305 and 50 000 rows (rank 0's GPU).
 
 After the timed regions every rank checks its shard's COMPLETE top-k against the CPU oracle run
 block-wise over the regenerated rows, and root checks the merged list (`parity_checked`).
@@ -42,6 +43,41 @@ ROWS_PER_GPU = 12_500_000      # 100 M rows / 8 GPUs (BASELINE.json configs[3]);
 ROWS_EXTRA = 1_000_000         # BASELINE.json configs[1]
 METRIC = "shard-queries/sec: queries/sec x row shards scanned per query (exact top-10 cosine, 768-d fp32)"
 UNIT = "shard-queries/s"
+
+
+def small_store_latency(bsr, device: int) -> dict:
+    """One search on a small resident store, end to end through the C ABI with host buffers (`bsr_search`
+    called through ctypes on preallocated arrays: what a Rust / C++ caller pays), query = row 0 of the store
+    (the reference's self-query, src/main.rs:111-120): median / 10th percentile of the per-call wall clock
+    and the launch's own duration (bsr_store_last_scan_ms).  2 305 rows is the reference's own store
+    (README.md:159), k = 50 its own top_k (src/main.rs:110); 50 000 rows is BASELINE.json configs[0]."""
+    from better_search_rag_rust_b200 import _lib
+    L = _lib.lib()
+    cases = []
+    for rows, kk in ((2305, 50), (2305, 10), (50_000, 10), (50_000, 50)):
+        st = bsr.GpuVectorstore(None, True, device=device, dim=DIM, capacity_rows=rows)
+        try:
+            st.append_synthetic(SEED, 0, rows)
+            q = np.ascontiguousarray(st.get(0).reshape(1, -1), dtype=np.float32)
+            oi, od = np.zeros((1, kk), np.uint64), np.zeros((1, kk), np.float32)
+            oc = np.zeros(1, np.uint32)
+            cargs = (st.handle, q.ctypes.data, 1, kk, oi.ctypes.data, od.ctypes.data, oc.ctypes.data)
+            for _ in range(50):
+                _lib.check(L.bsr_search(*cargs))
+            t = np.empty(1000)
+            for i in range(t.size):
+                t0 = time.perf_counter_ns()
+                L.bsr_search(*cargs)
+                t[i] = time.perf_counter_ns() - t0
+            ok = bool(oi[0, 0] == 0 and od[0, 0] == 0.0 and oc[0] == kk)
+            cases.append({"rows": rows, "dim": DIM, "k": kk, "e2e_us_median": float(np.median(t)) / 1e3,
+                          "e2e_us_p10": float(np.percentile(t, 10)) / 1e3,
+                          "queries_per_s": 1e9 / float(np.median(t)),
+                          "kernel_us": st.last_scan_ms() * 1e3, "self_query_first_at_distance_0": ok})
+        finally:
+            st.close()
+    return {"path": "bsr_search (C ABI, host buffers), per-call wall clock on rank 0, 1 000 calls per case",
+            "cases": cases}
 
 
 def parse_args():
@@ -548,6 +584,14 @@ def run_b200(args):
         line["extra_1m"] = {"config": workload_config(world, ROWS_EXTRA, k), "steps": extra["steps"], **se}
         if extra.get("sweeps"):
             line["extra_1m"]["sweeps"] = extra["sweeps"]
+    if not args.no_extra:
+        # BASELINE.json configs[0] and the reference's own store under the driver's clock: the latency of one
+        # search on a small store, rank 0's GPU only (the other ranks wait at the final barrier).  Never
+        # allowed to cost the line above: any failure is recorded, not raised.
+        try:
+            line["extra_small_stores"] = small_store_latency(bsr, local)
+        except Exception as e:
+            line["extra_small_stores"] = {"error": repr(e)}
     if world == 1 and not args.no_cpu_baseline:
         try:
             from oracle import c_oracle as co
