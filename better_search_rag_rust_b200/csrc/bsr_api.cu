@@ -738,7 +738,8 @@ static u32 bulk_max_qb(const bsr_store* s, u32 K) {
 // (evict-first) 29.0.  Stores above 1 GB gain less than the noise and keep the plain evict-first stream.
 static float l2_keep_fraction(const bsr_store* s, u32 n_panels) {
     if (s->kn.no_l2_keep || !s->l2_bytes) return 0.0f;
-    const double store_bytes = (double)n_panels * (double)panel_bytes(s);
+    // (n_panels counts 32-row panels, also for a bf16 store whose allocation unit is a 64-row tile)
+    const double store_bytes = (double)n_panels * 32.0 * (is_bf16(s) ? (double)s->kb * 128.0 : (double)s->dq * 16.0);
     const double keep = std::min(1.0, 0.60 * (double)s->l2_bytes / store_bytes);
     return store_bytes > 1e9 ? 0.0f : (float)keep;
 }
